@@ -1,0 +1,188 @@
+/*
+ * sglm_b200.h — C ABI of libsglm_b200.so: the B200 (sm_100a) hot path of sGLM
+ * (kimerein/sabatinilab-glm): lag/shift design-matrix gather, sufficient
+ * statistics (X'X, X'y, X'WX ...), batched penalised-GLM solvers and scoring.
+ *
+ * The reference has no FFI — its boundary is the Python API of backend/sglm_pp.py,
+ * backend/sglm.py and backend/sglm_cv.py, whose numerics are delegated to
+ * scikit-learn.  Each entry point below names the reference interface whose
+ * arithmetic it replaces (file:line relative to the reference tree; `sklearn/`
+ * = scikit-learn 1.9.0 as called from backend/sglm.py:241).  The Python mirror
+ * of the reference modules (sabatinilab-glm_b200/*.py) is the only caller;
+ * INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - the caller allocates everything, including workspaces sized by the
+ *     matching *_workspace_bytes();
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and
+ *     the call returns without synchronising;
+ *   - return value: 0 = ok, <0 = SGLM_E_*; sglm_last_error() gives the text of
+ *     the last failure on the calling thread; no C++ exception crosses the ABI;
+ *   - entry points are re-entrant (no global mutable state) and honour the
+ *     current CUDA device;
+ *   - matrices are row-major with explicit leading dimensions counted in elements.
+ */
+#ifndef SGLM_B200_H
+#define SGLM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGLM_OK 0
+#define SGLM_E_INVALID_ARG (-1)
+#define SGLM_E_SHAPE (-2)
+#define SGLM_E_ALIGN (-3)
+#define SGLM_E_WORKSPACE (-4)
+#define SGLM_E_CUDA (-5)
+#define SGLM_E_UNSUPPORTED (-6)
+
+/* version = major*10000 + minor*100 + patch */
+int sglm_version(void);
+const char *sglm_last_error(void);
+
+/* ------------------------------------------------------------------------- *
+ * (a1-a3) lag / shift gather.  Replaces sglm_pp.timeshift / shift /
+ * timeshift_multiple / concat_all_shifts (backend/sglm_pp.py:23-103, :298-357,
+ * :436-457):   out[t, c] = X[t - col_shift[c], col_src[c]]  if that row exists,
+ * else the 8-byte pattern `fill_bits` (np.nan = 0x7FF8000000000000).
+ * The column map (col_src, col_shift) encodes block order, the all-columns
+ * zero-shift block and keep_non_inx; it is built by the Python mirror.
+ * Elements are moved as opaque 8-byte words (bit-exact, NaN payloads kept).
+ * ------------------------------------------------------------------------- */
+int sglm_timeshift_f64(const double *X, int64_t T, int32_t n_cols_in, int64_t ldx,
+                       const int32_t *col_src, const int32_t *col_shift, int32_t n_cols_out,
+                       uint64_t fill_bits, double *out, int64_t ldo, void *stream);
+
+/* Same gather when the caller already knows min/max of col_shift (the Python mirror
+ * builds the map, so it does): no device read-back, never synchronises the stream. */
+int sglm_timeshift_f64_ranged(const double *X, int64_t T, int32_t n_cols_in, int64_t ldx,
+                              const int32_t *col_src, const int32_t *col_shift,
+                              int32_t n_cols_out, int32_t shift_min, int32_t shift_max,
+                              uint64_t fill_bits, double *out, int64_t ldo, void *stream);
+
+/* Row compaction that follows the gather in every caller (`dropna`,
+ * er_refactored_from_scratch_cleanup.py:429; backend/test/test_sglm_ez.py:28):
+ * out[r, :] = X[row_begin + r, :] for r < n_rows — a strided 2-D copy. */
+int sglm_crop_rows_f64(const double *X, int64_t ldx, int64_t row_begin, int64_t n_rows,
+                       int32_t n_cols, double *out, int64_t ldo, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * Sufficient statistics.  Replaces the X'X / X'y work that every sklearn fit
+ * repeats per (fold, alpha) (sklearn/linear_model/_ridge.py:215-227,
+ * _cd_fast.pyx:243-506 sweeps, _base.py:_preprocess_data) and the fancy-index
+ * fold copies of backend/sglm_cv.py:106-110.
+ *
+ * For each weight set s:  G[s] = Z' diag(w_s) Z   with  Z = [X | Y | 1]
+ * (n_aug = C + n_y + 1 columns), written as a full symmetric row-major matrix
+ * G[s][i*ldg + j], ldg >= n_aug.  So G[:C,:C] = X'WX, G[:C, C+k] = X'W y_k,
+ * G[:C, C+n_y] = sum w x,  G[C+k, C+k] = y_k'W y_k, G[n_aug-1, n_aug-1] = sum w.
+ * W is [n_sets][ldw] (row counts / IRLS weights); a NULL W means unit weights
+ * for every set.  ksplit_host[s] (host array, may be NULL) is the number of
+ * K-chunks set s is split into.
+ * ------------------------------------------------------------------------- */
+size_t sglm_suffstats_workspace_bytes(int64_t T, int32_t C, int32_t n_y, int32_t n_sets,
+                                      const int32_t *ksplit_host);
+int sglm_suffstats_f64(const double *X, int64_t ldx, const double *Y, int64_t ldy, int32_t n_y,
+                       int64_t T, int32_t C, const double *W, int64_t ldw, int32_t n_sets,
+                       const int32_t *ksplit_host, double *G, int64_t ldg, void *workspace,
+                       size_t workspace_bytes, void *stream);
+
+/* Index lists -> per-row multiplicities: counts[idx[i]] += 1 (the fold row sets of
+ * backend/sglm_cv.py:106-110, X[idx_train,:] / X[idx_test,:]).  counts must be zeroed. */
+int sglm_index_counts_f64(const int64_t *idx, int64_t n_idx, double *counts, int64_t T,
+                          void *stream);
+
+/* Centred problem from augmented statistics (sklearn _base.py:_preprocess_data +
+ * _pre_fit): with A = A_plus - A_minus (A_minus may be NULL), n = A[1,1],
+ * xbar = A[:C,1]/n, ybar = A[y,1]/n:
+ *   Qc = A[:C,:C] - n xbar xbar',  qc = A[:C,y] - n xbar ybar,  yyc = A[y,y] - n ybar^2
+ * (fit_intercept = 0: no centring, xbar = ybar = 0).  scal = {yyc, n, ybar, sum_y}. */
+int sglm_center_stats_f64(const double *A_plus, const double *A_minus, int64_t ldg, int32_t C,
+                          int32_t n_y, int32_t y_col, int32_t fit_intercept, double *Qc,
+                          int64_t ldq, double *qc, double *xbar, double *scal, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * (a6) batched Gram coordinate descent — ElasticNet / Lasso.  Replaces
+ * sklearn cd_fast.enet_coordinate_descent as reached from backend/sglm.py:106-110,
+ * :241 (sklearn/linear_model/_cd_fast.pyx:243-506; Gram form :1095-1290):
+ * cyclic order, soft threshold, trigger d_w_max/w_max <= tol, stop on
+ * gap <= tol*yy, gap-safe screening (sklearn 1.9), cold or warm start.
+ * One CTA of `warps_per_model` warps per model; many models resident per SM.
+ *   prob_Q[p], prob_q[p] : device arrays of device pointers; prob_yy[p] = yyc
+ *   model m uses problem prob_of_model[m] with l1_reg[m] = alpha*l1_ratio*n and
+ *   l2_reg[m] = alpha*(1-l1_ratio)*n  (_coordinate_descent.py:781-782).
+ *   W[m*ldw + j] is in/out when warm_start != 0, else out (started from 0).
+ *   info[m*4 + {0,1,2,3}] = {gap, tol*yy, n_iter, n_row_updates}.
+ * ------------------------------------------------------------------------- */
+int sglm_enet_cd_gram_f64(const double *const *prob_Q, const double *const *prob_q,
+                          const double *prob_yy, int64_t ldq, int32_t C,
+                          const int32_t *prob_of_model, const double *l1_reg,
+                          const double *l2_reg, const double *tol, const int32_t *max_iter,
+                          int32_t n_models, int32_t warm_start, int32_t do_screening,
+                          double *W, int64_t ldw, double *info, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * (a7, a8) batched Cholesky solve — Ridge / OLS.  Replaces sklearn
+ * _ridge._solve_cholesky (sklearn/linear_model/_ridge.py:215-227) and the
+ * full-rank case of LinearRegression (_base.py:700-756):
+ *   (Qc + alpha[k] I) w_k = qc   for k < n_alpha, one CTA per alpha.
+ * work holds n_alpha * (C+1) * ldq doubles.  status[k] = 0 ok, 1 = not positive
+ * definite (pivot <= 0).
+ * ------------------------------------------------------------------------- */
+size_t sglm_ridge_workspace_bytes(int32_t C, int64_t ldq, int32_t n_alpha);
+int sglm_ridge_solve_f64(const double *Qc, int64_t ldq, const double *qc, int32_t C,
+                         const double *alpha, int32_t n_alpha, double *W, int64_t ldw,
+                         int32_t *status, void *work, size_t work_bytes, void *stream);
+
+/* Intercepts and augmented evaluation vectors (sklearn _set_intercept,
+ * _coordinate_descent.py:1281):  b[m] = ybar[p] - xbar[p].w_m  (0 if xbar NULL)
+ *   V[m] = [-w_m | e_{y_col} | -b_m]  so that  RSS(set) = V[m]' G[set] V[m]. */
+int sglm_finalize_models_f64(const double *W, int64_t ldw, int32_t C, int32_t n_y,
+                             const int32_t *y_col_of_model, const double *const *xbar_of_model,
+                             const double *ybar_of_model, int32_t n_models, double *intercept,
+                             double *V, int64_t ldv, void *stream);
+
+/* (a11) scores from statistics: out[m] = V[m]' A V[m]  (A symmetric n x n). */
+int sglm_quadform_f64(const double *A, int64_t lda, int32_t n, const double *V, int64_t ldv,
+                      int32_t n_models, double *out, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * (a10, a11) explicit-matrix paths: GLM.predict / neg_mse_score / r2_score /
+ * get_residuals (backend/sglm.py:150-184, :314-347).  link: 0 identity, 1 log.
+ *   predict: out[t] = g^-1(X[t,:].w + b)
+ *   score:   sums[0..7] = { n, sum r^2, sum y, sum y^2, sum y*eta, sum mu,
+ *                           sum y log y, sum r }   with r = y - g^-1(eta), every term
+ *            weighted by the row multiplicity rw[t] (NULL = 1; selects a fold)
+ *            (resid may be NULL; else resid[t] = r).  ws: sglm_score_workspace_bytes().
+ * ------------------------------------------------------------------------- */
+int sglm_predict_f64(const double *X, int64_t ldx, int64_t T, int32_t C, const double *w,
+                     const double *b_dev, int32_t link, double *out, void *stream);
+size_t sglm_score_workspace_bytes(void);
+int sglm_score_f64(const double *X, int64_t ldx, const double *y, const double *rw, int64_t T,
+                   int32_t C, const double *w, const double *b_dev, int32_t link, double *resid,
+                   double *sums, void *workspace, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * (a9) Poisson IRLS step.  Replaces one iteration of the TweedieRegressor(power=1)
+ * optimisation (sklearn/linear_model/_glm/glm.py:185-339; Newton form
+ * _glm/_newton_solver.py) for objective mean(mu - y*eta) + alpha/2 |w|^2:
+ *   eta = X w + b, mu = exp(eta), weight[t] = rw[t]*mu, z[t] = eta + (y-mu)/mu,
+ *   sums[0..3] = { sum rw*(mu - y*eta), sum rw*mu, sum rw, sum rw*y }.
+ * rw (row multiplicity, may be NULL = 1) selects the fold.  The weighted
+ * statistics of [X | z | 1] then come from sglm_suffstats_f64 and the Newton
+ * system from sglm_center_stats_f64 + sglm_ridge_solve_f64.
+ * ------------------------------------------------------------------------- */
+int sglm_poisson_irls_prepare_f64(const double *X, int64_t ldx, const double *y, const double *rw,
+                                  int64_t T, int32_t C, const double *w, const double *b_dev,
+                                  double *weight, double *z, double *sums, void *workspace,
+                                  void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGLM_B200_H */

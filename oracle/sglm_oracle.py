@@ -55,7 +55,7 @@ def build_c_oracle(force: bool = False) -> str:
     if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
         os.makedirs(out_dir, exist_ok=True)
         subprocess.check_call(
-            ["gcc", "-O3", "-march=native", "-fPIC", "-shared", "-o", so, src, "-lm"]
+            ["gcc", "-O3", "-march=x86-64-v3", "-fPIC", "-shared", "-o", so, src, "-lm"]
         )
     return so
 

@@ -1,0 +1,424 @@
+"""
+Device-side orchestration of the sGLM hot path on one B200.
+
+Everything numeric happens in libsglm_b200.so (hand-written sm_100a kernels, see
+csrc/ and include/sglm_b200.h); this module only owns device buffers (torch tensors),
+the launch plan and the small host<->device transfers.  There is no CPU fallback.
+
+Launch plan for a CV grid (reference: backend/sglm_cv.py:42-428 — one sklearn fit per
+(param set, fold) from 4 Python threads, X[idx,:] copied per fold):
+
+  1. one pass over X per row set builds the augmented statistics G[s] = Z'diag(w_s)Z,
+     Z = [X | Y | 1]  (full data + each test fold; train = full - test, no fold copies);
+  2. per (fold, y column, fit_intercept) a centred problem (Qc, qc, yyc) is derived;
+  3. ALL ElasticNet/Lasso models of the grid run in ONE batched coordinate-descent launch
+     (one CTA per model), Ridge/OLS models in one Cholesky launch per problem;
+  4. intercepts, train/test RSS and TSS come from the statistics (quadratic forms), so
+     no model ever re-reads X.
+"""
+import ctypes
+
+import numpy as np
+
+import _sglm_native as nat
+from _sglm_native import call, ptr, stream_ptr
+
+_SM_TARGET_ITEMS = 148 * 8
+
+
+# --------------------------------------------------------------------------- #
+# host <-> device plumbing
+# --------------------------------------------------------------------------- #
+def is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _values(x):
+    """DataFrame / Series -> ndarray (reference: X.values, backend/sglm_ez.py:376-377)."""
+    if hasattr(x, "values") and not is_torch(x) and not isinstance(x, np.ndarray):
+        return x.values
+    return x
+
+
+def device_matrix(X):
+    """2-D float64 CUDA tensor with unit column stride (rows may be strided: views of a
+    larger design matrix are used as they are, no copy)."""
+    torch = nat.require_cuda()
+    X = _values(X)
+    if is_torch(X):
+        t = X
+        if t.dim() == 1:
+            t = t[:, None]
+        if t.dtype != torch.float64:
+            t = t.to(torch.float64)
+        if not t.is_cuda:
+            t = t.to("cuda", non_blocking=True)
+        if t.dim() != 2:
+            raise ValueError(f"Expected 2D array, got {t.dim()}D")
+        if t.shape[1] > 0 and t.stride(1) != 1 or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
+            t = t.contiguous()
+        return t
+    a = np.asarray(X)
+    if a.ndim == 1:
+        a = a.reshape(-1, 1)
+    if a.ndim != 2:
+        raise ValueError(f"Expected 2D array, got {a.ndim}D array instead")
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return torch.from_numpy(a).to("cuda")
+
+
+def device_vector(y):
+    torch = nat.require_cuda()
+    y = _values(y)
+    if is_torch(y):
+        t = y.reshape(-1)
+        if t.dtype != torch.float64:
+            t = t.to(torch.float64)
+        if not t.is_cuda:
+            t = t.to("cuda", non_blocking=True)
+        return t.contiguous()
+    a = np.ascontiguousarray(np.asarray(y).reshape(-1), dtype=np.float64)
+    return torch.from_numpy(a).to("cuda")
+
+
+def row_stride(t):
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1)
+
+
+def _empty(shape, dtype=None):
+    torch = nat.require_cuda()
+    return torch.empty(shape, dtype=dtype or torch.float64, device="cuda")
+
+
+def _zeros(shape, dtype=None):
+    torch = nat.require_cuda()
+    return torch.zeros(shape, dtype=dtype or torch.float64, device="cuda")
+
+
+def _dev(a, dtype):
+    torch = nat.require_cuda()
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).to("cuda")
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+# --------------------------------------------------------------------------- #
+# (a1-a3) gather
+# --------------------------------------------------------------------------- #
+def gather(Xd, col_src, col_shift, fill_value):
+    """out[t, c] = Xd[t - col_shift[c], col_src[c]] or fill (sglm_timeshift_f64_ranged)."""
+    T, P = Xd.shape
+    col_src = np.ascontiguousarray(col_src, dtype=np.int32)
+    col_shift = np.ascontiguousarray(col_shift, dtype=np.int32)
+    C = int(col_src.shape[0])
+    out = _empty((T, C))
+    if T == 0 or C == 0:
+        return out
+    if col_src.min() < 0 or col_src.max() >= P:
+        raise IndexError("shift_inx out of bounds for the columns of X")
+    both = _dev(np.concatenate([col_src, col_shift]), np.int32)
+    call("sglm_timeshift_f64_ranged", ptr(Xd), T, P, row_stride(Xd), ptr(both[:C]), ptr(both[C:]), C,
+         int(col_shift.min()), int(col_shift.max()), nat.f64_bits(fill_value), ptr(out), C, stream_ptr())
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# sufficient statistics
+# --------------------------------------------------------------------------- #
+def index_counts(idx, T):
+    """Row multiplicities of an index list (X[idx, :] semantics incl. repeats / negatives)."""
+    torch = nat.require_cuda()
+    counts = _zeros((T,))
+    if is_torch(idx):
+        it = idx.to(device="cuda", dtype=torch.int64).contiguous()
+    else:
+        a = np.asarray(idx)
+        if a.dtype == bool:
+            a = np.flatnonzero(a)
+        it = _dev(a.reshape(-1), np.int64)
+    if it.numel():
+        call("sglm_index_counts_f64", ptr(it), it.numel(), ptr(counts), T, stream_ptr())
+    return counts
+
+
+def suffstats(Xd, Yd, W=None, rows_hint=None):
+    """G[s] = Z' diag(W[s]) Z with Z = [X | Y | 1].  W: [n_sets, T] tensor or None (one
+    unit-weight set).  Returns G [n_sets, n_aug, ldg] (full symmetric)."""
+    T, C = Xd.shape
+    n_y = Yd.shape[1]
+    n_sets = 1 if W is None else W.shape[0]
+    n_aug = C + n_y + 1
+    ldg = _round_up(n_aug, 8)
+    G = _empty((n_sets, n_aug, ldg))
+    n_tiles = max(1, (T + 15) // 16)
+    n_pairs = ((n_aug + 127) // 128) * (((n_aug + 127) // 128) + 1) // 2
+    rows = np.asarray(rows_hint if rows_hint is not None else [T] * n_sets, dtype=np.float64)
+    rows = np.maximum(rows, 1.0)
+    ks = np.maximum(1, np.minimum(np.maximum(1, (rows / 16).astype(np.int64) // 64),
+                                  np.rint(_SM_TARGET_ITEMS * rows / rows.sum() / n_pairs).astype(np.int64)))
+    ks = np.ascontiguousarray(np.minimum(ks, n_tiles), dtype=np.int32)
+    ks_p = ks.ctypes.data_as(ctypes.c_void_p)
+    ws_bytes = nat.lib().sglm_suffstats_workspace_bytes(T, C, n_y, n_sets, ks_p)
+    if ws_bytes == 0:
+        raise nat.SglmNativeError("suffstats: invalid plan: " + nat.lib().sglm_last_error().decode())
+    torch = nat.require_cuda()
+    ws = torch.empty((ws_bytes + 255) // 256 * 32, dtype=torch.float64, device="cuda")
+    call("sglm_suffstats_f64", ptr(Xd), row_stride(Xd), ptr(Yd), row_stride(Yd), n_y, T, C,
+         ptr(W), (W.stride(0) if W is not None else 0), n_sets, ks_p, ptr(G), ldg, ptr(ws), ws.numel() * 8,
+         stream_ptr())
+    return G
+
+
+class Problem:
+    """Centred problem (Qc, qc, yyc, xbar, ybar, n) of one (row set, y column, intercept)."""
+    __slots__ = ("Qc", "qc", "xbar", "scal", "ldq", "fit_intercept", "y_col", "n", "ybar", "yyc", "sy")
+
+
+def center(A_plus, A_minus, C, n_y, y_col, fit_intercept):
+    ldg = A_plus.stride(0)
+    ldq = _round_up(C, 8)
+    p = Problem()
+    p.Qc = _empty((C, ldq))
+    p.qc = _empty((C,))
+    p.xbar = _empty((C,))
+    p.scal = _empty((4,))
+    p.ldq, p.fit_intercept, p.y_col = ldq, bool(fit_intercept), y_col
+    call("sglm_center_stats_f64", ptr(A_plus), ptr(A_minus), ldg, C, n_y, y_col, int(bool(fit_intercept)),
+         ptr(p.Qc), ldq, ptr(p.qc), ptr(p.xbar), ptr(p.scal), stream_ptr())
+    return p
+
+
+def fetch_scalars(problems):
+    """One D2H copy for the (yyc, n, ybar, sum_y) of all problems."""
+    torch = nat.require_cuda()
+    if not problems:
+        return
+    host = torch.stack([p.scal for p in problems]).cpu().numpy()
+    for p, s in zip(problems, host):
+        p.yyc, p.n, p.ybar, p.sy = (float(v) for v in s)
+
+
+# --------------------------------------------------------------------------- #
+# batched solvers
+# --------------------------------------------------------------------------- #
+class ModelSpec:
+    """One fit of the grid: which problem, which penalty."""
+    __slots__ = ("problem", "kind", "alpha", "l1_ratio", "max_iter", "tol", "coef_init")
+
+    def __init__(self, problem, kind, alpha=1.0, l1_ratio=0.5, max_iter=1000, tol=1e-4, coef_init=None):
+        self.problem, self.kind = problem, kind
+        self.alpha, self.l1_ratio = float(alpha), float(l1_ratio)
+        self.max_iter, self.tol, self.coef_init = int(max_iter), float(tol), coef_init
+
+
+def solve_models(models, C, do_screening=True):
+    """Solve every model; returns (W [M, ldw] device, info [M,4] host or None, status list).
+    ElasticNet/Lasso: one batched coordinate-descent launch.  Ridge/OLS: one Cholesky
+    launch per problem (one CTA per alpha)."""
+    torch = nat.require_cuda()
+    M = len(models)
+    ldw = _round_up(C, 2)
+    W = _zeros((M, ldw))
+    info = np.zeros((M, 4))
+    status = np.zeros(M, dtype=np.int64)
+    cd = [i for i, m in enumerate(models) if m.kind in ("lasso", "enet")]
+    if cd:
+        # longest-running (small penalty) models first so the tail of the launch is short
+        cd.sort(key=lambda i: (models[i].alpha * max(models[i].l1_ratio, 1e-3)))
+        probs, pidx = [], {}
+        for i in cd:
+            p = models[i].problem
+            if id(p) not in pidx:
+                pidx[id(p)] = len(probs)
+                probs.append(p)
+        ldq = probs[0].ldq
+        Qp = _dev(np.array([p.Qc.data_ptr() for p in probs], dtype=np.uint64).view(np.int64), np.int64)
+        qp = _dev(np.array([p.qc.data_ptr() for p in probs], dtype=np.uint64).view(np.int64), np.int64)
+        yy = _dev([p.yyc for p in probs], np.float64)
+        warm = any(models[i].coef_init is not None for i in cd)
+        l1 = [(models[i].alpha * models[i].l1_ratio * models[i].problem.n) for i in cd]
+        l2 = [(models[i].alpha * (1.0 - models[i].l1_ratio) * models[i].problem.n) for i in cd]
+        pack_f = _dev(np.array([l1, l2, [models[i].tol for i in cd]], dtype=np.float64), np.float64)
+        pack_i = _dev(np.array([[pidx[id(models[i].problem)] for i in cd],
+                                [models[i].max_iter for i in cd]], dtype=np.int32), np.int32)
+        Wcd = _zeros((len(cd), ldw))
+        if warm:
+            init = np.zeros((len(cd), ldw))
+            for r, i in enumerate(cd):
+                if models[i].coef_init is not None:
+                    init[r, :C] = np.asarray(models[i].coef_init, dtype=np.float64).reshape(-1)
+            Wcd.copy_(torch.from_numpy(init))
+        info_d = _empty((len(cd), 4))
+        call("sglm_enet_cd_gram_f64", ptr(Qp), ptr(qp), ptr(yy), ldq, C, ptr(pack_i[0]), ptr(pack_f[0]),
+             ptr(pack_f[1]), ptr(pack_f[2]), ptr(pack_i[1]), len(cd), int(warm), int(do_screening),
+             ptr(Wcd), ldw, ptr(info_d), stream_ptr())
+        cd_t = _dev(cd, np.int64)
+        W.index_copy_(0, cd_t, Wcd)
+        info[cd] = info_d.cpu().numpy()
+        status[cd] = (info[cd, 0] > info[cd, 1]).astype(np.int64)      # 1 = duality gap above tolerance
+    groups = {}
+    for i, m in enumerate(models):
+        if m.kind in ("ridge", "ols"):
+            groups.setdefault(id(m.problem), []).append(i)
+    for idxs in groups.values():
+        p = models[idxs[0]].problem
+        alphas = _dev([0.0 if models[i].kind == "ols" else models[i].alpha for i in idxs], np.float64)
+        n_a = len(idxs)
+        wb = nat.lib().sglm_ridge_workspace_bytes(C, p.ldq, n_a)
+        work = torch.empty(wb // 8, dtype=torch.float64, device="cuda")
+        Wr = _empty((n_a, ldw))
+        st = torch.empty(n_a, dtype=torch.int32, device="cuda")
+        call("sglm_ridge_solve_f64", ptr(p.Qc), p.ldq, ptr(p.qc), C, ptr(alphas), n_a, ptr(Wr), ldw, ptr(st),
+             ptr(work), wb, stream_ptr())
+        W.index_copy_(0, _dev(idxs, np.int64), Wr)
+        status[idxs] = st.cpu().numpy() * 2                            # 2 = not positive definite
+        del work
+    return W, info, status
+
+
+def finalize(W, C, n_y, models):
+    """Intercepts b = ybar - xbar.w and evaluation vectors V = [-w | e_y | -b]."""
+    M = len(models)
+    ldw = W.stride(0)
+    ldv = _round_up(C + n_y + 1, 2)
+    V = _empty((M, ldv))
+    b = _empty((M,))
+    ycol = _dev([m.problem.y_col for m in models], np.int32)
+    xb = _dev(np.array([m.problem.xbar.data_ptr() for m in models], dtype=np.uint64).view(np.int64), np.int64)
+    yb = _dev([m.problem.ybar for m in models], np.float64)
+    call("sglm_finalize_models_f64", ptr(W), ldw, C, n_y, ptr(ycol), ptr(xb), ptr(yb), M, ptr(b), ptr(V), ldv,
+         stream_ptr())
+    return b, V
+
+
+def quadform(A, V):
+    """out[m] = V[m]' A V[m]."""
+    M = V.shape[0]
+    out = _empty((M,))
+    n = A.shape[0]
+    if M:
+        call("sglm_quadform_f64", ptr(A), A.stride(0), n, ptr(V), V.stride(0), M, ptr(out), stream_ptr())
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# explicit-matrix passes
+# --------------------------------------------------------------------------- #
+def _coef_dev(coef, intercept):
+    w = _dev(np.asarray(coef, dtype=np.float64).reshape(-1), np.float64)
+    b = _dev([float(np.asarray(intercept).reshape(-1)[0])], np.float64)
+    return w, b
+
+
+def predict(Xd, coef, intercept, link=0):
+    T, C = Xd.shape
+    w, b = _coef_dev(coef, intercept)
+    if w.numel() != C:
+        raise ValueError(f"X has {C} features, but the model was fitted with {w.numel()} features")
+    out = _empty((T,))
+    call("sglm_predict_f64", ptr(Xd), row_stride(Xd), T, C, ptr(w), ptr(b), link, ptr(out), stream_ptr())
+    return out
+
+
+def score_sums(Xd, yd, coef, intercept, link=0, rw=None, want_resid=False):
+    """Fused pass: {n, sum r^2, sum y, sum y^2, sum y*eta, sum mu, sum y log y, sum r} (host)."""
+    torch = nat.require_cuda()
+    T, C = Xd.shape
+    w, b = _coef_dev(coef, intercept)
+    if w.numel() != C:
+        raise ValueError(f"X has {C} features, but the model was fitted with {w.numel()} features")
+    sums = _empty((8,))
+    ws = torch.empty(nat.lib().sglm_score_workspace_bytes() // 8, dtype=torch.float64, device="cuda")
+    resid = _empty((T,)) if want_resid else None
+    call("sglm_score_f64", ptr(Xd), row_stride(Xd), ptr(yd), ptr(rw), T, C, ptr(w), ptr(b), link, ptr(resid),
+         ptr(sums), ptr(ws), stream_ptr())
+    return sums.cpu().numpy(), resid
+
+
+def r2_from_sums(s):
+    n, rss, sy, syy = s[0], s[1], s[2], s[3]
+    tss = syy - sy * sy / n
+    if tss <= 0.0:
+        return 1.0 if rss == 0.0 else 0.0
+    return float(1.0 - rss / tss)
+
+
+def poisson_d2_from_sums(s):
+    """D^2 = 1 - dev/dev_null (sklearn _glm/glm.py:387-463) from the fused sums."""
+    n, sy, sy_eta, smu, sylogy = s[0], s[2], s[4], s[5], s[6]
+    dev = 2.0 * (sylogy - sy_eta - sy + smu)
+    ybar = sy / n
+    dev_null = 2.0 * (sylogy - sy * np.log(ybar)) if ybar > 0 else 0.0
+    return float(1.0 - dev / dev_null)
+
+
+# --------------------------------------------------------------------------- #
+# (a9) Poisson by IRLS (Newton) — weighted statistics on the tensor path, Cholesky step
+# --------------------------------------------------------------------------- #
+def poisson_irls(Xd, yd, alpha, fit_intercept=True, rw=None, max_iter=100, tol=1e-4, coef_init=None,
+                 intercept_init=None):
+    """argmin mean(mu - y*eta) + alpha/2 |w|^2 (rows weighted by multiplicity rw).
+    Newton/IRLS with step halving; stops when the Newton step is below
+    min(tol, 1e-8) * max(1, |w|_inf) — i.e. at the optimum the reference's L-BFGS
+    (gtol = tol) is heading for.  Returns (coef ndarray, intercept, n_iter)."""
+    torch = nat.require_cuda()
+    T, C = Xd.shape
+    ldw = _round_up(C, 2)
+    sums = _empty((8,))
+    ws = torch.empty(nat.lib().sglm_score_workspace_bytes() // 8, dtype=torch.float64, device="cuda")
+    weight = _empty((1, T))
+    z = _empty((T, 1))
+    if rw is None:
+        n_tot, ysum = float(T), float(yd.sum().item())
+    else:
+        n_tot, ysum = float(rw.sum().item()), float((rw * yd).sum().item())
+    if not (ysum > 0):
+        raise ValueError("Some value(s) of y are out of the valid range of the loss 'HalfPoissonLoss'.")
+    w = _zeros((ldw,))
+    b = _zeros((1,))
+    if coef_init is not None:
+        w[:C] = _dev(np.asarray(coef_init, dtype=np.float64).reshape(-1), np.float64)
+        if fit_intercept and intercept_init is not None:
+            b[0] = float(intercept_init)
+    elif fit_intercept:
+        b[0] = float(np.log(ysum / n_tot))
+    step_tol = min(tol, 1e-8)
+    w_prev, b_prev, f_prev = None, None, np.inf
+    n_iter, halvings = 0, 0
+    rows_hint = [n_tot]
+    alphas = _dev([alpha * n_tot], np.float64)
+    wb = nat.lib().sglm_ridge_workspace_bytes(C, _round_up(C, 8), 1)
+    work = torch.empty(wb // 8, dtype=torch.float64, device="cuda")
+    st = torch.empty(1, dtype=torch.int32, device="cuda")
+    while True:
+        call("sglm_poisson_irls_prepare_f64", ptr(Xd), row_stride(Xd), ptr(yd), ptr(rw), T, C, ptr(w), ptr(b),
+             ptr(weight), ptr(z), ptr(sums), ptr(ws), stream_ptr())
+        f = float(sums[0].item()) / n_tot + 0.5 * alpha * float((w[:C] * w[:C]).sum().item())
+        if w_prev is not None and not (f <= f_prev + 1e-12 * max(1.0, abs(f_prev))) and halvings < 30:
+            w = 0.5 * (w + w_prev)
+            b = 0.5 * (b + b_prev)
+            halvings += 1
+            continue
+        halvings = 0
+        if n_iter >= max_iter:
+            break
+        G = suffstats(Xd, z, weight, rows_hint)
+        p = center(G[0], None, C, 1, 0, fit_intercept)
+        w_new = _zeros((1, ldw))
+        call("sglm_ridge_solve_f64", ptr(p.Qc), p.ldq, ptr(p.qc), C, ptr(alphas), 1, ptr(w_new), ldw, ptr(st),
+             ptr(work), wb, stream_ptr())
+        fetch_scalars([p])
+        b_new = _zeros((1,))
+        if fit_intercept:
+            b_new[0] = p.ybar - float((p.xbar * w_new[0, :C]).sum().item())
+        n_iter += 1
+        dw = float((w_new[0, :C] - w[:C]).abs().max().item())
+        db = float((b_new - b).abs().max().item())
+        scale = max(1.0, float(w_new[0, :C].abs().max().item()))
+        w_prev, b_prev, f_prev = w, b, f
+        w, b = w_new[0].clone(), b_new
+        if max(dw, db) <= step_tol * scale:
+            break
+    return w[:C].cpu().numpy(), float(b.item()) if fit_intercept else 0.0, n_iter

@@ -1,0 +1,118 @@
+"""
+ctypes binding of libsglm_b200.so (the C ABI declared in include/sglm_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device is
+present when a compute entry point is called, this module raises.  PyTorch is used
+only for device memory, streams and host<->device copies.
+"""
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsglm_b200.so")
+
+c_i32, c_i64, c_u64, c_f64 = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_double
+c_vp, c_sz = ctypes.c_void_p, ctypes.c_size_t
+
+_PROTOTYPES = {
+    "sglm_version": (c_i32, []),
+    "sglm_last_error": (ctypes.c_char_p, []),
+    "sglm_timeshift_f64": (c_i32, [c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_i32, c_u64, c_vp, c_i64, c_vp]),
+    "sglm_timeshift_f64_ranged": (c_i32, [c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_i32, c_i32, c_i32,
+                                          c_u64, c_vp, c_i64, c_vp]),
+    "sglm_crop_rows_f64": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_i64, c_vp]),
+    "sglm_suffstats_workspace_bytes": (c_sz, [c_i64, c_i32, c_i32, c_i32, c_vp]),
+    "sglm_suffstats_f64": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_i64, c_i32,
+                                   c_vp, c_vp, c_i64, c_vp, c_sz, c_vp]),
+    "sglm_index_counts_f64": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp]),
+    "sglm_center_stats_f64": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64,
+                                      c_vp, c_vp, c_vp, c_vp]),
+    "sglm_enet_cd_gram_f64": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                      c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp]),
+    "sglm_ridge_workspace_bytes": (c_sz, [c_i32, c_i64, c_i32]),
+    "sglm_ridge_solve_f64": (c_i32, [c_vp, c_i64, c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp, c_vp,
+                                     c_sz, c_vp]),
+    "sglm_finalize_models_f64": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp,
+                                         c_vp, c_i64, c_vp]),
+    "sglm_quadform_f64": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_vp, c_vp]),
+    "sglm_predict_f64": (c_i32, [c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp]),
+    "sglm_score_workspace_bytes": (c_sz, []),
+    "sglm_score_f64": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp,
+                               c_vp, c_vp]),
+    "sglm_poisson_irls_prepare_f64": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp,
+                                              c_vp, c_vp, c_vp, c_vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+_launches = 0          # number of kernel-launching ABI calls made through this binding (bench.py reads it)
+
+
+class SglmNativeError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libsglm_b200.so (once).  Raises if it has not been built."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise SglmNativeError(
+                    f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` "
+                    "(nvcc, sm_100a).  There is no CPU fallback.")
+            handle = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in _PROTOTYPES.items():
+                fn = getattr(handle, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = handle
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_PROTOTYPES)
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise SglmNativeError("sglm_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point; raise with sglm_last_error() on failure."""
+    global _launches
+    rc = getattr(lib(), name)(*args)
+    if rc != 0:
+        msg = lib().sglm_last_error()
+        raise SglmNativeError(f"{name} failed (code {rc}): {msg.decode() if msg else ''}")
+    _launches += 1
+    return rc
+
+
+def launches():
+    return _launches
+
+
+NAN_BITS = int(np.array([np.nan], dtype=np.float64).view(np.uint64)[0])
+
+
+def f64_bits(value):
+    return int(np.array([value], dtype=np.float64).view(np.uint64)[0])

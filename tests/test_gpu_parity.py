@@ -1,0 +1,423 @@
+"""GPU parity tests: the CUDA path (through the Python mirror and the C ABI of
+libsglm_b200.so) against the oracle and the golden fixtures produced from the unmodified
+reference.  Tolerances: design matrices bit-exact; coefficients rel 1e-4
+(||dw||_inf / ||w||_inf) at identical tol/max_iter, direct solvers 1e-7; scores abs 1e-6."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import coef_rel_err, load_golden
+from oracle import sglm_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+import _engine as eng  # noqa: E402
+import _sglm_native as nat  # noqa: E402
+import sglm  # noqa: E402
+import sglm_cv  # noqa: E402
+import sglm_ez  # noqa: E402
+import sglm_pp  # noqa: E402
+
+
+def _kw(kwargs):
+    kw = dict(kwargs)
+    if kw.get("fill_value") == "nan":
+        kw["fill_value"] = np.nan
+    return kw
+
+
+def _design(blob):
+    Xd = orc.timeshift_multiple(blob["X0"], shift_amt_list=[int(s) for s in blob["shifts"]])
+    return Xd[blob["keep"]]
+
+
+# ------------------------------------------------------------------ gather
+def test_gather_golden_bit_exact():
+    blob, meta = load_golden("gather_ref")
+    for i, case in enumerate(meta["cases"]):
+        X, want = blob[f"x{i}"], blob[f"r{i}"]
+        kw = _kw(case["kwargs"])
+        got = sglm_pp.timeshift_multiple(X, **kw) if "shift_amt_list" in kw else sglm_pp.timeshift(X, **kw)
+        assert got.shape == want.shape, case["name"]
+        assert got.dtype == want.dtype, case["name"]
+        assert got.tobytes() == want.tobytes(), case["name"]
+
+
+def test_gather_reference_unit_tests_dataframe():
+    """backend/test/test_sglm_pp.py:115-151 re-stated against the drop-in module."""
+    _, meta = load_golden("gather_ref")
+    df = pd.DataFrame(np.arange(20).reshape(5, 4), columns=list("ABCD"))
+    a = np.arange(20).reshape(5, 4)
+    r1 = sglm_pp.timeshift_multiple(df, shift_amt_list=[-1, 0, 1], unshifted_keep_all=True, fill_value=0)
+    assert list(r1.columns) == meta["df_names_all"]
+    assert np.all(r1.values == orc.timeshift_multiple(a, shift_amt_list=[-1, 0, 1], fill_value=0))
+    inx = sglm_pp.get_column_nums(df, ["A", "D"])
+    r2 = sglm_pp.timeshift_multiple(df, shift_inx=inx, shift_amt_list=[-1, 0, 1], fill_value=0)
+    assert list(r2.columns) == meta["df_names_sub"]
+    assert np.all(r2.values == orc.timeshift_multiple(a, shift_inx=[0, 3], shift_amt_list=[-1, 0, 1], fill_value=0))
+    r3 = sglm_pp.timeshift(df, shift_inx=inx, shift_amt=1, fill_value=0, keep_non_inx=True)
+    assert list(r3.columns) == list("ABCD")
+    assert np.all(r3.values == orc.timeshift(a, shift_inx=[0, 3], shift_amt=1, fill_value=0, keep_non_inx=True))
+    assert np.all(sglm_pp.timeshift(df, shift_amt=0) == df)
+    with pytest.raises(ValueError):
+        sglm_pp.get_column_nums(pd.DataFrame(np.zeros((2, 2)), columns=["A", "A"]), ["A"])
+
+
+@pytest.mark.parametrize("T,P,h,inx", [(5000, 7, 12, [0, 2, 5]), (4097, 10, 20, []), (300, 3, 1, [1]),
+                                       (2048, 33, 5, list(range(0, 33, 2)))])
+def test_gather_random_vs_oracle_bit_exact(T, P, h, inx):
+    rng = np.random.default_rng(T + P)
+    X = rng.standard_normal((T, P))
+    X[rng.integers(0, T, 20), rng.integers(0, P, 20)] = np.nan
+    shifts = [0] + list(range(-h, 0)) + list(range(1, h + 1))
+    want = orc.timeshift_multiple(X, shift_inx=inx, shift_amt_list=shifts)
+    got = sglm_pp.timeshift_multiple(X, shift_inx=inx, shift_amt_list=shifts)
+    assert got.tobytes() == want.tobytes()
+    got_t = sglm_pp.timeshift_multiple(torch.from_numpy(X).cuda(), shift_inx=inx, shift_amt_list=shifts)
+    assert got_t.is_cuda and got_t.cpu().numpy().tobytes() == want.tobytes()
+
+
+def test_gather_nan_payload_and_negative_zero_preserved():
+    X = np.zeros((64, 2))
+    bits = X.view(np.uint64)
+    bits[5, 0] = 0x7FF8DEADBEEF0001      # NaN with a payload
+    bits[6, 1] = 0x8000000000000000      # -0.0
+    got = sglm_pp.timeshift(X, shift_amt=3)
+    want = orc.timeshift(X, shift_amt=3)
+    assert got.tobytes() == want.tobytes()
+    assert got.view(np.uint64)[8, 0] == 0x7FF8DEADBEEF0001
+    assert got.view(np.uint64)[0, 0] == nat.NAN_BITS
+
+
+def test_gather_direct_kernel_paths():
+    """Very wide source (window does not fit shared memory) and |shift| >= T use the direct kernel."""
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((257, 3000))
+    shifts = [0, -40, 40, 7]
+    want = orc.timeshift_multiple(X, shift_inx=[0, 1500, 2999], shift_amt_list=shifts)
+    got = sglm_pp.timeshift_multiple(X, shift_inx=[0, 1500, 2999], shift_amt_list=shifts)
+    assert got.tobytes() == want.tobytes()
+    Y = rng.standard_normal((10, 4))
+    for a in (10, -10, 25, 9, -9):
+        assert sglm_pp.timeshift(Y, shift_amt=a).tobytes() == orc.timeshift(Y, shift_amt=a).tobytes()
+
+
+def test_gather_generic_abi_entry_and_strided_source():
+    """sglm_timeshift_f64 (range recovered on device) + a row-strided source view."""
+    rng = np.random.default_rng(9)
+    big = torch.from_numpy(rng.standard_normal((500, 12))).cuda()
+    view = big[:, 2:9]                               # ldx = 12, 7 columns
+    src = np.array([0, 3, 6, 1], dtype=np.int32)
+    sh = np.array([0, 2, -3, 5], dtype=np.int32)
+    d = torch.from_numpy(np.concatenate([src, sh])).cuda()
+    out = torch.empty((500, 4), dtype=torch.float64, device="cuda")
+    nat.call("sglm_timeshift_f64", nat.ptr(view), 500, 7, 12, nat.ptr(d[:4]), nat.ptr(d[4:]), 4,
+             nat.NAN_BITS, nat.ptr(out), 4, nat.stream_ptr())
+    want = orc.timeshift_c(view.cpu().numpy(), src, sh)
+    assert out.cpu().numpy().tobytes() == want.tobytes()
+
+
+def test_gather_roundtrip_property_full_size_rows():
+    """shift by +k then by -k restores the interior rows (size-independent property)."""
+    T, P, k = 200_000, 8, 17
+    X = torch.randn((T, P), dtype=torch.float64, device="cuda")
+    back = sglm_pp.shift(sglm_pp.shift(X, k), -k)
+    assert torch.equal(back[: T - k], X[: T - k])
+    assert bool(torch.isnan(back[T - k:]).all())
+
+
+def test_concat_crop_helpers():
+    rng = np.random.default_rng(2)
+    X = rng.standard_normal((9, 3))
+    blanks = rng.standard_normal((2, 3))
+    assert np.array_equal(sglm_pp.concat_start_crop_end(blanks, X), np.concatenate([blanks, X])[:-2])
+    assert np.array_equal(sglm_pp.concat_end_crop_start(blanks, X), np.concatenate([X, blanks])[2:])
+
+
+# ------------------------------------------------------------------ statistics
+@pytest.mark.parametrize("T,C,n_y,weighted,ld_pad", [(3000, 45, 1, False, 0), (2500, 130, 2, True, 0),
+                                                      (1000, 37, 1, True, 3), (70, 300, 1, False, 1),
+                                                      (5, 4, 1, False, 0)])
+def test_suffstats_vs_numpy(T, C, n_y, weighted, ld_pad):
+    rng = np.random.default_rng(T * 7 + C)
+    Xfull = rng.standard_normal((T, C + ld_pad)) + 0.3
+    X = Xfull[:, :C]
+    Y = rng.standard_normal((T, n_y))
+    Xd = torch.from_numpy(Xfull).cuda()[:, :C]
+    Yd = torch.from_numpy(Y).cuda()
+    Z = np.concatenate([X, Y, np.ones((T, 1))], axis=1)
+    if weighted:
+        W = np.stack([np.ones(T), (rng.random(T) < 0.2).astype(float), rng.integers(0, 3, T).astype(float)])
+        W[1, : T // 2] = 0.0                         # long all-zero stretch -> skipped tiles
+        G = eng.suffstats(Xd, Yd, torch.from_numpy(W).cuda(), [T, W[1].sum(), W[2].sum()])
+        want = np.stack([(Z * w[:, None]).T @ Z for w in W])
+    else:
+        G = eng.suffstats(Xd, Yd)
+        want = (Z.T @ Z)[None]
+    n_aug = C + n_y + 1
+    got = G[:, :, :n_aug].cpu().numpy()
+    scale = np.abs(want).max()
+    assert np.max(np.abs(got - want)) <= 1e-12 * scale
+    assert np.array_equal(got, np.transpose(got, (0, 2, 1)))          # exactly symmetric
+
+
+def test_index_counts_matches_bincount():
+    rng = np.random.default_rng(4)
+    idx = rng.integers(-50, 1000, 5000)
+    got = eng.index_counts(idx, 1000).cpu().numpy()
+    want = np.bincount(np.where(idx < 0, idx + 1000, idx), minlength=1000).astype(float)
+    assert np.array_equal(got, want)
+
+
+# ------------------------------------------------------------------ solvers on statistics
+def test_cd_kernel_matches_oracle_gram_cd_iterate_for_iterate():
+    rng = np.random.default_rng(11)
+    n, p = 4000, 60
+    X = rng.standard_normal((n, p)) @ (np.eye(p) + 0.5 * rng.standard_normal((p, p)) / np.sqrt(p))
+    X[:, 7] = 0.0                                     # zero column (Q[j,j] == 0 branch)
+    y = X @ (rng.standard_normal(p) * (rng.random(p) < 0.4)) + rng.standard_normal(n)
+    for alpha, l1r, tol, mi in [(0.05, 0.5, 1e-4, 1000), (0.5, 1.0, 1e-4, 1000), (1e-3, 0.1, 1e-8, 1000),
+                                (0.02, 0.9, 1e-4, 2)]:
+        w_o, b_o, info_o = orc.enet_fit(X, y, alpha, l1r, True, mi, tol, use_gram=True)
+        est = sglm.ElasticNet(alpha=alpha, l1_ratio=l1r, tol=tol, max_iter=mi)
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            est.fit(X, y)
+        assert est.n_iter_ == info_o["n_iter"], (alpha, l1r, est.n_iter_, info_o)
+        assert coef_rel_err(est.coef_, w_o) < 1e-9
+        assert abs(est.intercept_ - b_o) < 1e-9
+
+
+def test_ridge_cholesky_multi_tile_vs_numpy():
+    rng = np.random.default_rng(13)
+    n, p = 3000, 203                                   # > 3 tiles of 64, ragged 32-blocks
+    X = rng.standard_normal((n, p)) + 1.0
+    y = rng.standard_normal(n)
+    for alpha in (1e-3, 1.0, 1e3):
+        for fi in (True, False):
+            w_o, b_o = orc.ridge_fit(X, y, alpha, fi)
+            g = sglm.GLM("Gaussian", alpha=alpha, l1_ratio=0, fit_intercept=fi, max_iter=10)
+            g.fit(X, y)
+            assert coef_rel_err(g.coef_, w_o) < 1e-9, (alpha, fi)
+            assert abs(g.intercept_ - b_o) < 1e-9
+
+
+def test_fits_vs_reference_golden():
+    blob, meta = load_golden("fits_ref")
+    Xd, y = _design(blob), blob["y"]
+    n_iter_mismatch = 0
+    import warnings
+    for i, kw in enumerate(meta["grid"]):
+        g = sglm.GLM("Gaussian", **dict(kw))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            g.fit(Xd, y)
+        kind = g.model.kind
+        lim = 1e-4 if kind in ("lasso", "enet") else 1e-7
+        assert coef_rel_err(g.coef_, blob["coefs"][i]) < lim, (kw, coef_rel_err(g.coef_, blob["coefs"][i]))
+        assert abs(g.intercept_ - blob["intercepts"][i]) < 1e-6 * max(1.0, abs(blob["intercepts"][i])), kw
+        assert abs(g.r2_score(Xd, y) - blob["r2"][i]) < 1e-6, kw
+        assert abs(g.neg_mse_score(Xd, y) - blob["neg_mse"][i]) < 1e-6, kw
+        if kind in ("lasso", "enet") and blob["n_iter"][i] > 0:
+            n_iter_mismatch += int(g.model.n_iter_ != blob["n_iter"][i])
+    assert n_iter_mismatch == 0
+
+
+def test_predict_score_residuals_vs_numpy():
+    rng = np.random.default_rng(21)
+    X = rng.standard_normal((1501, 33))
+    y = rng.standard_normal(1501)
+    g = sglm.GLM("Gaussian", alpha=0.01, l1_ratio=0.5)
+    g.fit(X, y)
+    pred = X @ g.coef_ + g.intercept_
+    assert np.allclose(g.predict(X), pred, rtol=0, atol=1e-12)
+    assert np.allclose(g.predict(pd.DataFrame(X)), pred, rtol=0, atol=1e-12)
+    r, mr = g.get_residuals(X, y)
+    assert np.allclose(r, y - pred, atol=1e-12) and np.allclose(mr, y - y.mean(), atol=1e-12)
+    assert abs(g.neg_mse_score(X, y) + np.mean((y - pred) ** 2)) < 1e-12
+    assert abs(g.r2_score(X, y) - orc.r2_score(y, pred)) < 1e-12
+    assert abs(sglm.calc_R2(r, mr) - orc.calc_R2(y - pred, y - y.mean())) < 1e-12
+
+
+def test_warm_start_matches_oracle():
+    rng = np.random.default_rng(31)
+    X = rng.standard_normal((2000, 25))
+    y = X[:, :5].sum(1) + rng.standard_normal(2000)
+    beta = rng.standard_normal(25) * 0.1
+    w_o, b_o, info = orc.enet_fit(X, y, 0.05, 0.5, True, 1000, 1e-4, coef_init=beta, use_gram=True)
+    g = sglm.GLM("Gaussian", beta_=beta, beta0_=0.0, alpha=0.05, l1_ratio=0.5)
+    g.fit(X, y)
+    assert g.model.n_iter_ == info["n_iter"]
+    assert coef_rel_err(g.coef_, w_o) < 1e-9
+
+
+def test_error_behaviour():
+    X = np.random.default_rng(0).standard_normal((50, 3))
+    y = np.arange(50.0)
+    Xn = X.copy()
+    Xn[3, 1] = np.nan
+    with pytest.raises(ValueError):
+        sglm.GLM("Gaussian", alpha=0.1, l1_ratio=0.5).fit(Xn, y)
+    with pytest.raises(ValueError):
+        sglm.GLM("Gaussian", alpha=0.1, l1_ratio=0.5).fit(X, y[:-1])
+    with pytest.raises(KeyError):
+        sglm.GLM("Gaussian", alpha=0)
+    with pytest.raises(TypeError):
+        sglm.GLM("Gaussian", reg_lambda=0.1)                    # backend/test/test_sglm.py:25 (stale kwarg)
+    with pytest.raises(NameError):
+        sglm.GLM("NoSuchFamily")
+
+
+# ------------------------------------------------------------------ Poisson
+def test_poisson_vs_sklearn_optimum_golden():
+    blob, meta = load_golden("poisson_ref")
+    Xd, y = _design(blob), blob["y"]
+    for i, kw in enumerate(meta["grid"]):
+        g = sglm.GLM("Poisson", **dict(kw))
+        g.fit(Xd, y)                                    # the reference raises AttributeError here
+        assert coef_rel_err(g.coef_, blob["coefs"][i]) < 1e-6, (kw, coef_rel_err(g.coef_, blob["coefs"][i]))
+        assert abs(g.intercept_ - blob["intercepts"][i]) < 1e-7, kw
+        assert abs(g.r2_score(Xd, y) - blob["d2"][i]) < 1e-6, kw
+        mu = np.exp(Xd @ g.coef_ + g.intercept_)
+        assert np.allclose(g.predict(Xd), mu, rtol=1e-12)
+        assert abs(g.neg_mse_score(Xd, y) + np.mean((y - mu) ** 2)) < 1e-10
+
+
+# ------------------------------------------------------------------ CV grid
+def test_cv_grid_vs_reference_golden():
+    blob, meta = load_golden("cv_ref")
+    Xd, y = _design(blob), blob["y"]
+    cv_idx = [(blob[f"train{k}"], blob[f"test{k}"]) for k in range(meta["n_folds"])]
+    for run in meta["runs"]:
+        tag = run["tag"]
+        kw_lst = [dict(k) for k in run["kwargs"]]
+        res = sglm_cv.cv_glm_mult_params(Xd, y, cv_idx, "Gaussian", kw_lst, score_method=run["score_method"])
+        assert res["best_params"] == run["best_params"], tag
+        assert abs(res["best_score"] - run["best_score"]) < 1e-6, tag
+        assert abs(res["best_score_std"] - run["best_score_std"]) < 1e-6, tag
+        assert all("roll" not in k and "model_name" not in k for k in kw_lst)     # popped in place
+        for j, r in enumerate(res["full_cv_results"]):
+            assert r["glm_kwargs"] == run["result_kwargs"][j]
+            assert list(r)[:11] == ['cv_coefs', 'cv_intercepts', 'cv_scores_train', 'cv_scores_test',
+                                    'cv_mean_score_train', 'cv_mean_score', 'cv_std_score', 'cv_R2_score',
+                                    'cv_mse_score', 'glm_kwargs', 'model']
+            for k in range(meta["n_folds"]):
+                assert coef_rel_err(r["cv_coefs"][:, k], blob[f"{tag}_coefs{j}"][:, k]) < 1e-4, (tag, j, k)
+            assert np.allclose(r["cv_intercepts"], blob[f"{tag}_icpt{j}"], atol=1e-6)
+            assert np.allclose(r["cv_scores_train"], blob[f"{tag}_tr{j}"], atol=1e-6), (tag, j)
+            assert np.allclose(r["cv_scores_test"], blob[f"{tag}_te{j}"], atol=1e-6), (tag, j)
+            agg = [r["cv_mean_score_train"], r["cv_mean_score"], r["cv_std_score"], r["cv_R2_score"],
+                   r["cv_mse_score"]]
+            assert np.allclose(agg, blob[f"{tag}_agg{j}"], atol=1e-6), (tag, j)
+            assert coef_rel_err(r["model"].coef_, blob[f"{tag}_fullcoef{j}"]) < 1e-4
+            assert abs(r["model"].intercept_ - float(blob[f"{tag}_fullicpt{j}"])) < 1e-6
+            # the returned model object predicts and scores
+            assert r["model"].predict(Xd[:7]).shape == (7,)
+
+
+def test_cv_grid_vs_oracle_overlapping_and_repeated_indices():
+    """Train sets that are not the complement of the test sets and repeated rows."""
+    rng = np.random.default_rng(77)
+    X0 = orc.synth_base(1500, 4, 77)
+    shifts = [0, -2, -1, 1, 2]
+    Xd = orc.timeshift_multiple(X0, shift_amt_list=shifts)[2:-2]
+    y = orc.synth_response(Xd, orc.synth_kernels(4, shifts, 77), 77)
+    n = Xd.shape[0]
+    cv_idx = []
+    for _ in range(3):
+        perm = rng.permutation(n)
+        train = np.concatenate([perm[:900], perm[:100]])           # 100 rows twice
+        test = perm[850:1300]                                      # overlaps train
+        cv_idx.append((train, test))
+    grid = [dict(alpha=0.01, l1_ratio=0.5, max_iter=1000, fit_intercept=True),
+            dict(alpha=1.0, l1_ratio=0, max_iter=1000, fit_intercept=True),
+            dict(alpha=0.1, l1_ratio=1, max_iter=1000, fit_intercept=False)]
+    want = orc.cv_glm_mult_params(Xd, y, cv_idx, "Gaussian", [dict(g) for g in grid], score_method="r2")
+    got = sglm_cv.cv_glm_mult_params(Xd, y, cv_idx, "Gaussian", [dict(g) for g in grid], score_method="r2")
+    assert got["best_params"] == want["best_params"]
+    for a, b in zip(got["full_cv_results"], want["full_cv_results"]):
+        for k in range(3):
+            assert coef_rel_err(a["cv_coefs"][:, k], b["cv_coefs"][:, k]) < 1e-4
+        assert np.allclose(a["cv_scores_test"], b["cv_scores_test"], atol=1e-6)
+        assert np.allclose(a["cv_scores_train"], b["cv_scores_train"], atol=1e-6)
+        assert abs(a["cv_R2_score"] - b["cv_R2_score"]) < 1e-6
+        assert abs(a["cv_mse_score"] - b["cv_mse_score"]) < 1e-6
+
+
+def test_cv_single_params_and_poisson_cv_vs_oracle():
+    X0 = orc.synth_base(1200, 3, 8)
+    shifts = [0, -1, 1]
+    Xd = orc.timeshift_multiple(X0, shift_amt_list=shifts)[1:-1]
+    beta = orc.synth_kernels(3, shifts, 8)
+    y = orc.synth_response(Xd, beta, 8)
+    cv_idx = orc.synth_folds(Xd.shape[0], 3, seed=8, group=100)
+    kw = dict(alpha=0.01, l1_ratio=0.3, max_iter=500, roll=3)
+    resp = []
+    got = sglm_cv.cv_glm_single_params(Xd, y, cv_idx, "Gaussian", kw, resp_list=resp, score_method="mse")
+    assert resp and resp[0] is got and "roll" not in kw
+    want = orc.cv_glm_single_params(Xd, y, cv_idx, "Gaussian", dict(alpha=0.01, l1_ratio=0.3, max_iter=500, roll=3))
+    assert np.allclose(got["cv_scores_test"], want["cv_scores_test"], atol=1e-6)
+    assert coef_rel_err(got["model"].coef_, want["model"].coef_) < 1e-4
+    yp = orc.synth_response(Xd, beta, 8, poisson=True)
+    gp = sglm_cv.cv_glm_single_params(Xd, yp, cv_idx, "Poisson", dict(alpha=0.01), score_method="r2", resp_list=[])
+    wp = orc.cv_glm_single_params(Xd, yp, cv_idx, "Poisson", dict(alpha=0.01), score_method="r2")
+    for k in range(3):
+        assert coef_rel_err(gp["cv_coefs"][:, k], wp["cv_coefs"][:, k]) < 1e-6
+    assert np.allclose(gp["cv_scores_test"], wp["cv_scores_test"], atol=1e-6)
+    assert abs(gp["cv_R2_score"] - wp["cv_R2_score"]) < 1e-6
+
+
+def test_reference_integration_flow_repaired():
+    """backend/test/test_sglm_ez.py:19-74 with its stale unpacking repaired (5-tuple)."""
+    X_tmp = pd.DataFrame(np.arange(200).reshape((100, 2)), columns=['A', 'B'])
+    X_tmp['B'] = (X_tmp['B'] - 1) * 2 + 1
+    X_tmp = sglm_ez.timeshift_cols(X_tmp, ['A'], pos_order=2)
+    assert list(X_tmp.columns) == ['A', 'B', 'A_1', 'A_2']
+    X_tmp = sglm_ez.diff_cols(X_tmp, ['A', 'B']).dropna()
+    glm = sglm_ez.fit_GLM(X_tmp[['A']], X_tmp['B'], alpha=0.1)
+    ref = orc.GLM("Gaussian", alpha=0.1).fit(X_tmp[['A']].values, X_tmp['B'].values)
+    assert coef_rel_err(glm.coef_, ref.coef_) < 1e-4
+    np.random.seed(0)
+    cv_idx = sglm_ez.cv_idx_by_timeframe(X_tmp, y=None, num_folds=None, timesteps_per_bucket=20)
+    lst = sglm_cv.generate_mult_params({'alpha': reversed([0.1, 1.0, 10.0]), 'l1_ratio': [0.1, 0.5, 0.9],
+                                        'fit_intercept': [True, False]}, {'max_iter': 10000})
+    assert len(lst) == 18
+    best_score, best_std, best_params, best_model, cv_results = sglm_ez.simple_cv_fit(
+        X_tmp[['A']], X_tmp['B'], cv_idx, lst, model_type='Normal')
+    want = orc.cv_glm_mult_params(X_tmp[['A']].values, X_tmp['B'].values, cv_idx, "Gaussian",
+                                  sglm_cv.generate_mult_params({'alpha': reversed([0.1, 1.0, 10.0]),
+                                                                'l1_ratio': [0.1, 0.5, 0.9],
+                                                                'fit_intercept': [True, False]}, {'max_iter': 10000}))
+    assert best_params == want["best_params"]
+    assert abs(best_score - want["best_score"]) < 1e-6 * max(1.0, abs(want["best_score"]))
+    ols = orc.GLM("Gaussian", alpha=0, l1_ratio=0, max_iter=1).fit(X_tmp[['A']].values, X_tmp['B'].values)
+    assert abs(ols.intercept_ - best_model.intercept_) < 0.01
+    assert np.all(np.abs(ols.coef_ - best_model.coef_) < 0.01)
+    glm2, hs, hm = sglm_ez.training_fit_holdout_score(X_tmp[['A']], X_tmp['B'], X_tmp[['A']], X_tmp['B'], best_params)
+    assert hs > 0.99 and hm <= 0.0
+
+
+def test_train_stats_identity_at_scale():
+    """Size-independent property at a larger size: G(full) == G(test) + G(train) and the CV
+    scores computed from statistics match an explicit pass over X."""
+    T, C = 60_000, 96
+    X = torch.randn((T, C), dtype=torch.float64, device="cuda")
+    y = torch.randn((T,), dtype=torch.float64, device="cuda")
+    m = (torch.rand(T, device="cuda") < 0.2).double()
+    W = torch.stack([torch.ones_like(m), m, 1.0 - m])
+    G = eng.suffstats(X, y[:, None], W, [T, float(m.sum()), float(T - m.sum())])
+    err = (G[0] - G[1] - G[2]).abs().max().item()
+    assert err <= 1e-9 * G[0].abs().max().item()
+    Xh, yh = X.cpu().numpy(), y.cpu().numpy()
+    test = np.flatnonzero(m.cpu().numpy() > 0)
+    train = np.flatnonzero(m.cpu().numpy() == 0)
+    r = sglm_cv.cv_glm_single_params(X, y, [(train, test)], "Gaussian", dict(alpha=0.01, l1_ratio=0.5),
+                                     score_method="r2", resp_list=[])
+    w, b = r["cv_coefs"][:, 0], r["cv_intercepts"][0]
+    assert abs(r["cv_scores_test"][0] - orc.r2_score(yh[test], Xh[test] @ w + b)) < 1e-9
+    assert abs(r["cv_scores_train"][0] - orc.r2_score(yh[train], Xh[train] @ w + b)) < 1e-9
