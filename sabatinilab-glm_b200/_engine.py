@@ -151,7 +151,7 @@ def suffstats(Xd, Yd, W=None, rows_hint=None):
     n_sets = 1 if W is None else W.shape[0]
     n_aug = C + n_y + 1
     ldg = _round_up(n_aug, 8)
-    G = _empty((n_sets, n_aug, ldg))
+    G = _zeros((n_sets, n_aug, ldg))       # padding columns stay zero
     n_tiles = max(1, (T + 15) // 16)
     n_pairs = ((n_aug + 127) // 128) * (((n_aug + 127) // 128) + 1) // 2
     rows = np.asarray(rows_hint if rows_hint is not None else [T] * n_sets, dtype=np.float64)

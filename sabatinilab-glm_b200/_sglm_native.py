@@ -96,14 +96,48 @@ def ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+# kernels launched per ABI call (for the launch count bench.py reports)
+_KERNELS_PER_CALL = {"sglm_suffstats_f64": 3, "sglm_score_f64": 2, "sglm_poisson_irls_prepare_f64": 2,
+                     "sglm_timeshift_f64": 2}
+_timing = None         # when enabled: list of (name, start_event, end_event) on the current stream
+
+
+def enable_timing(on=True):
+    """Bracket every ABI call with CUDA events on the launching stream (bench.py only)."""
+    global _timing
+    _timing = [] if on else None
+
+
+def collect_timing():
+    """-> {entry point: (calls, total ms)}; synchronises.  Clears the record."""
+    import torch
+    global _timing
+    out = {}
+    if _timing:
+        torch.cuda.synchronize()
+        for name, e0, e1 in _timing:
+            c, t = out.get(name, (0, 0.0))
+            out[name] = (c + 1, t + e0.elapsed_time(e1))
+        _timing = []
+    return out
+
+
 def call(name, *args):
     """Invoke an int-returning entry point; raise with sglm_last_error() on failure."""
     global _launches
+    if _timing is not None:
+        import torch
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = getattr(lib(), name)(*args)
     if rc != 0:
         msg = lib().sglm_last_error()
         raise SglmNativeError(f"{name} failed (code {rc}): {msg.decode() if msg else ''}")
-    _launches += 1
+    if _timing is not None:
+        e1.record()
+        _timing.append((name, e0, e1))
+    _launches += _KERNELS_PER_CALL.get(name, 1)
     return rc
 
 

@@ -64,7 +64,7 @@ def test_gather_reference_unit_tests_dataframe():
     assert np.all(r3.values == orc.timeshift(a, shift_inx=[0, 3], shift_amt=1, fill_value=0, keep_non_inx=True))
     assert np.all(sglm_pp.timeshift(df, shift_amt=0) == df)
     with pytest.raises(ValueError):
-        sglm_pp.get_column_nums(pd.DataFrame(np.zeros((2, 2)), columns=["A", "A"]), ["A"])
+        sglm_pp.get_column_nums(pd.DataFrame(np.zeros((2, 3)), columns=["A", "B", "A"]), ["A"])
 
 
 @pytest.mark.parametrize("T,P,h,inx", [(5000, 7, 12, [0, 2, 5]), (4097, 10, 20, []), (300, 3, 1, [1]),
