@@ -101,10 +101,12 @@ int sglm_index_counts_f64(const int64_t *idx, int64_t n_idx, double *counts, int
  * _pre_fit): with A = A_plus - A_minus (A_minus may be NULL), n = A[1,1],
  * xbar = A[:C,1]/n, ybar = A[y,1]/n:
  *   Qc = A[:C,:C] - n xbar xbar',  qc = A[:C,y] - n xbar ybar,  yyc = A[y,y] - n ybar^2
- * (fit_intercept = 0: no centring, xbar = ybar = 0).  scal = {yyc, n, ybar, sum_y}. */
+ * (fit_intercept = 0: no centring, xbar = ybar = 0).  diag[i] = Qc[i,i] (compact copy for
+ * the coordinate-descent kernel).  scal = {yyc, n, ybar, sum_y}. */
 int sglm_center_stats_f64(const double *A_plus, const double *A_minus, int64_t ldg, int32_t C,
                           int32_t n_y, int32_t y_col, int32_t fit_intercept, double *Qc,
-                          int64_t ldq, double *qc, double *xbar, double *scal, void *stream);
+                          int64_t ldq, double *qc, double *xbar, double *diag, double *scal,
+                          void *stream);
 
 /* ------------------------------------------------------------------------- *
  * (a6) batched Gram coordinate descent — ElasticNet / Lasso.  Replaces
@@ -112,15 +114,17 @@ int sglm_center_stats_f64(const double *A_plus, const double *A_minus, int64_t l
  * :241 (sklearn/linear_model/_cd_fast.pyx:243-506; Gram form :1095-1290):
  * cyclic order, soft threshold, trigger d_w_max/w_max <= tol, stop on
  * gap <= tol*yy, gap-safe screening (sklearn 1.9), cold or warm start.
- * One CTA of `warps_per_model` warps per model; many models resident per SM.
- *   prob_Q[p], prob_q[p] : device arrays of device pointers; prob_yy[p] = yyc
+ * One CTA (1-8 warps, by C) per model, several models resident per SM; the rows of Q a
+ * model is about to need are prefetched into a shared-memory ring with cp.async.
+ *   prob_Q[p], prob_q[p], prob_diag[p] : device arrays of device pointers (Qc, qc,
+ *   diag(Qc) from sglm_center_stats_f64); prob_yy[p] = yyc
  *   model m uses problem prob_of_model[m] with l1_reg[m] = alpha*l1_ratio*n and
  *   l2_reg[m] = alpha*(1-l1_ratio)*n  (_coordinate_descent.py:781-782).
  *   W[m*ldw + j] is in/out when warm_start != 0, else out (started from 0).
- *   info[m*4 + {0,1,2,3}] = {gap, tol*yy, n_iter, n_row_updates}.
+ *   info[m*6 + {0..5}] = {gap, tol*yy, n_iter, n_row_updates, n_rows_fetched, 0}.
  * ------------------------------------------------------------------------- */
 int sglm_enet_cd_gram_f64(const double *const *prob_Q, const double *const *prob_q,
-                          const double *prob_yy, int64_t ldq, int32_t C,
+                          const double *const *prob_diag, const double *prob_yy, int64_t ldq, int32_t C,
                           const int32_t *prob_of_model, const double *l1_reg,
                           const double *l2_reg, const double *tol, const int32_t *max_iter,
                           int32_t n_models, int32_t warm_start, int32_t do_screening,

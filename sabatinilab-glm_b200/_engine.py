@@ -173,7 +173,7 @@ def suffstats(Xd, Yd, W=None, rows_hint=None):
 
 class Problem:
     """Centred problem (Qc, qc, yyc, xbar, ybar, n) of one (row set, y column, intercept)."""
-    __slots__ = ("Qc", "qc", "xbar", "scal", "ldq", "fit_intercept", "y_col", "n", "ybar", "yyc", "sy")
+    __slots__ = ("Qc", "qc", "xbar", "diag", "scal", "ldq", "fit_intercept", "y_col", "n", "ybar", "yyc", "sy")
 
 
 def center(A_plus, A_minus, C, n_y, y_col, fit_intercept):
@@ -183,10 +183,11 @@ def center(A_plus, A_minus, C, n_y, y_col, fit_intercept):
     p.Qc = _empty((C, ldq))
     p.qc = _empty((C,))
     p.xbar = _empty((C,))
+    p.diag = _empty((C,))
     p.scal = _empty((4,))
     p.ldq, p.fit_intercept, p.y_col = ldq, bool(fit_intercept), y_col
     call("sglm_center_stats_f64", ptr(A_plus), ptr(A_minus), ldg, C, n_y, y_col, int(bool(fit_intercept)),
-         ptr(p.Qc), ldq, ptr(p.qc), ptr(p.xbar), ptr(p.scal), stream_ptr())
+         ptr(p.Qc), ldq, ptr(p.qc), ptr(p.xbar), ptr(p.diag), ptr(p.scal), stream_ptr())
     return p
 
 
@@ -221,7 +222,7 @@ def solve_models(models, C, do_screening=True):
     M = len(models)
     ldw = _round_up(C, 2)
     W = _zeros((M, ldw))
-    info = np.zeros((M, 4))
+    info = np.zeros((M, 6))
     status = np.zeros(M, dtype=np.int64)
     cd = [i for i, m in enumerate(models) if m.kind in ("lasso", "enet")]
     if cd:
@@ -236,6 +237,7 @@ def solve_models(models, C, do_screening=True):
         ldq = probs[0].ldq
         Qp = _dev(np.array([p.Qc.data_ptr() for p in probs], dtype=np.uint64).view(np.int64), np.int64)
         qp = _dev(np.array([p.qc.data_ptr() for p in probs], dtype=np.uint64).view(np.int64), np.int64)
+        dp = _dev(np.array([p.diag.data_ptr() for p in probs], dtype=np.uint64).view(np.int64), np.int64)
         yy = _dev([p.yyc for p in probs], np.float64)
         warm = any(models[i].coef_init is not None for i in cd)
         l1 = [(models[i].alpha * models[i].l1_ratio * models[i].problem.n) for i in cd]
@@ -250,8 +252,8 @@ def solve_models(models, C, do_screening=True):
                 if models[i].coef_init is not None:
                     init[r, :C] = np.asarray(models[i].coef_init, dtype=np.float64).reshape(-1)
             Wcd.copy_(torch.from_numpy(init))
-        info_d = _empty((len(cd), 4))
-        call("sglm_enet_cd_gram_f64", ptr(Qp), ptr(qp), ptr(yy), ldq, C, ptr(pack_i[0]), ptr(pack_f[0]),
+        info_d = _empty((len(cd), 6))
+        call("sglm_enet_cd_gram_f64", ptr(Qp), ptr(qp), ptr(dp), ptr(yy), ldq, C, ptr(pack_i[0]), ptr(pack_f[0]),
              ptr(pack_f[1]), ptr(pack_f[2]), ptr(pack_i[1]), len(cd), int(warm), int(do_screening),
              ptr(Wcd), ldw, ptr(info_d), stream_ptr())
         cd_t = _dev(cd, np.int64)

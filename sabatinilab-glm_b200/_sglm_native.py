@@ -29,8 +29,8 @@ _PROTOTYPES = {
                                    c_vp, c_vp, c_i64, c_vp, c_sz, c_vp]),
     "sglm_index_counts_f64": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp]),
     "sglm_center_stats_f64": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64,
-                                      c_vp, c_vp, c_vp, c_vp]),
-    "sglm_enet_cd_gram_f64": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                      c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "sglm_enet_cd_gram_f64": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp,
                                       c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp]),
     "sglm_ridge_workspace_bytes": (c_sz, [c_i32, c_i64, c_i32]),
     "sglm_ridge_solve_f64": (c_i32, [c_vp, c_i64, c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp, c_vp,

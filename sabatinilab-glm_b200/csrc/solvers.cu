@@ -8,7 +8,7 @@
 //
 // Roofline of the CD kernel: memory (rows of Q streamed from L2/HBM).  Algorithmic bytes
 // per model = 8*C per coordinate update that changes w (one row of Q) — the kernel counts
-// those updates (info[4m+3]) so bench.py can report sum(bytes)/time.
+// those updates (info[6m+3]) so bench.py can report sum(bytes)/time.
 #include <algorithm>
 
 #include "common.cuh"
@@ -19,7 +19,8 @@ namespace sglm {
 __global__ void __launch_bounds__(256)
 center_stats_kernel(const double *__restrict__ Ap, const double *__restrict__ Am, long long ldg, int C,
                     int n_y, int y_col, int fit_intercept, double *__restrict__ Qc, long long ldq,
-                    double *__restrict__ qc, double *__restrict__ xbar, double *__restrict__ scal) {
+                    double *__restrict__ qc, double *__restrict__ xbar, double *__restrict__ diag,
+                    double *__restrict__ scal) {
     const int one = C + n_y, yc = C + y_col;
     auto A = [&](int i, int j) {
         double v = Ap[(long long)i * ldg + j];
@@ -38,6 +39,7 @@ center_stats_kernel(const double *__restrict__ Ap, const double *__restrict__ Am
             v = A(i, j) - n * xi * xj;
         }
         Qc[(long long)i * ldq + j] = v;
+        if (j == i) diag[i] = v;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         qc[i] = A(i, yc) - n * xi * ybar;
@@ -79,66 +81,71 @@ __device__ __forceinline__ void cta_reduce(double (&v)[K], double *scratch) {
     }
 }
 
-template <int NW>
-__global__ void __launch_bounds__(NW * 32)
+constexpr int CD_CH = 4;   // 16-byte chunks of Qw owned by one thread per pass of the panel update
+
+// One CTA (NW warps) per model.  Cyclic coordinate descent is sequential — coordinate j+1
+// needs the Qw produced by coordinate j — so a one-coordinate-at-a-time kernel is bound by
+// the latency of its own instruction chain (measured: ~2400 cycles per update, ncu
+// profiles/r1_v2_cd_one_*).  The sweep is therefore blocked 32 coordinates at a time:
+//
+//   phase 1 (warp 0, registers + shuffles only): lane l owns coordinate j_l of the block,
+//     its Qw[j_l] and the column Q[j_0..j_31][j_l] of the 32x32 diagonal sub-block; the 32
+//     coordinates are visited in order, each delta is broadcast with a shuffle and folded
+//     into the other lanes' Qw[j_l] — the exact FMA sequence of the unblocked algorithm;
+//   phase 2 (all warps): the 32 deltas are applied to all of Qw at once,
+//     Qw[k] = fma(delta_i, Q[j_i][k], Qw[k]) for i in block order (again the same FMA
+//     sequence per element), streaming only the rows whose coefficient moved, many
+//     independent 16-byte loads in flight per thread — this is the HBM/L2-bound part.
+//
+// The iterates are bit-identical to the one-coordinate-at-a-time formulation; only the
+// schedule changes.  Shared memory per model: w, Qw, the active list (no copy of Q).
+template <int NB, int CD_RG, int MINB>
+__global__ void __launch_bounds__((NB + 1) * 32, MINB)
 enet_cd_gram_kernel(const double *const *__restrict__ prob_Q, const double *const *__restrict__ prob_q,
-                    const double *__restrict__ prob_yy, long long ldq, int C,
-                    const int *__restrict__ prob_of_model, const double *__restrict__ l1_reg,
-                    const double *__restrict__ l2_reg, const double *__restrict__ tol_in,
-                    const int *__restrict__ max_iter_in, int warm_start, int do_screening,
-                    double *__restrict__ W, long long ldw, double *__restrict__ info) {
+                    const double *const *__restrict__ prob_diag, const double *__restrict__ prob_yy,
+                    long long ldq, int C, const int *__restrict__ prob_of_model,
+                    const double *__restrict__ l1_reg, const double *__restrict__ l2_reg,
+                    const double *__restrict__ tol_in, const int *__restrict__ max_iter_in, int warm_start,
+                    int do_screening, double *__restrict__ W, long long ldw, double *__restrict__ info) {
+    constexpr int NW = NB + 1;              // warp 0: sequential phase; warps 1..NB: panel update
     constexpr int NT = NW * 32;
+    constexpr int NTB = NB * 32;
     extern __shared__ __align__(16) double sm[];
     const int Cp = (C + 1) & ~1;
-    double *w = sm;                 // [Cp]
-    double *Qw = w + Cp;            // [Cp]
-    double *qs = Qw + Cp;           // [Cp]
-    double *ds = qs + Cp;           // [Cp]
-    double *scratch = ds + Cp;      // [NW * 8]
-    int *active = reinterpret_cast<int *>(scratch + NW * 8);          // [C]
-    int *iscr = active + C;                                            // [NW + 1]
-    unsigned char *state = reinterpret_cast<unsigned char *>(iscr + NW + 1);  // [C] 0 live, 2 to-drop
+    double *w = sm;                         // [Cp]
+    double *Qw = w + Cp;                    // [Cp]  (element C, when C is odd, is a harmless pad)
+    double *scratch = Qw + Cp;              // [NW * 8]
+    double *dlt = scratch + NW * 8;         // [32] deltas of the rows to stream (compacted)
+    int *active = reinterpret_cast<int *>(dlt + 32);                           // [C]
+    int *jb = active + C;                                                      // [32] their coordinates
+    int *iscr = jb + 32;                                                       // [NW + 2]
+    unsigned char *state = reinterpret_cast<unsigned char *>(iscr + NW + 2);   // [C] 2 = to-drop
 
     const int m = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pid = prob_of_model[m];
     const double *__restrict__ Q = prob_Q[pid];
     const double *__restrict__ q = prob_q[pid];
+    const double *__restrict__ dg = prob_diag[pid];
     const double yy = prob_yy[pid];
     const double l1 = l1_reg[m], l2 = l2_reg[m];
     const double d_w_tol = tol_in[m];
     const double tol = d_w_tol * yy;
     const int max_iter = max_iter_in[m];
-    const bool vec2 = ((ldq & 1) == 0) && ((reinterpret_cast<uintptr_t>(Q) & 15) == 0);
-    const int C2 = C >> 1;
-    long long n_upd = 0;
+    const bool vec2 = ((ldq & 1) == 0) && ((reinterpret_cast<uintptr_t>(Q) & 15) == 0) && (ldq >= Cp);
+    const int Cp2 = Cp >> 1;
+    long long n_upd = 0, n_blk = 0;
 
-    // Qw += a * Q[j, :]
+    // Qw += a * Q[j, :]   (single-row path: warm start, screening drops)
     auto axpy_row = [&](int j, double a) {
         const double *row = Q + (long long)j * ldq;
-        if (vec2) {
-            const double2 *row2 = reinterpret_cast<const double2 *>(row);
-            double2 *Qw2 = reinterpret_cast<double2 *>(Qw);
 #pragma unroll 8
-            for (int k = tid; k < C2; k += NT) {
-                const double2 r = __ldg(row2 + k);
-                double2 t = Qw2[k];
-                t.x += a * r.x;
-                t.y += a * r.y;
-                Qw2[k] = t;
-            }
-            if ((C & 1) && tid == 0) Qw[C - 1] += a * __ldg(row + C - 1);
-        } else {
-#pragma unroll 8
-            for (int k = tid; k < C; k += NT) Qw[k] += a * __ldg(row + k);
-        }
+        for (int k = tid; k < C; k += NT) Qw[k] += a * __ldg(row + k);
     };
 
-    for (int j = tid; j < C; j += NT) {
-        w[j] = warm_start ? W[(long long)m * ldw + j] : 0.0;
+    for (int j = tid; j < Cp; j += NT) {
+        w[j] = (warm_start && j < C) ? W[(long long)m * ldw + j] : 0.0;
         Qw[j] = 0.0;
-        qs[j] = q[j];
-        ds[j] = Q[(long long)j * ldq + j];
-        state[j] = 0;
+        if (j < C) state[j] = 0;
     }
     cta_sync<NW>();
     if (warm_start) {
@@ -154,7 +161,7 @@ enet_cd_gram_kernel(const double *const *__restrict__ prob_Q, const double *cons
     auto compute_gap = [&]() -> double {
         double v[6] = {0, 0, 0, 0, 0, 0};   // ww, wq, wQw, |w|_1, sum xta^2, max |xta|
         for (int j = tid; j < C; j += NT) {
-            const double wj = w[j], Qwj = Qw[j], qj = qs[j];
+            const double wj = w[j], Qwj = Qw[j], qj = __ldg(q + j);
             v[0] += wj * wj;
             v[1] += wj * qj;
             v[2] += wj * Qwj;
@@ -181,6 +188,7 @@ enet_cd_gram_kernel(const double *const *__restrict__ prob_Q, const double *cons
 
     const bool screening = do_screening && (l1 != 0.0);
     int n_active = C;
+    for (int j = tid; j < C; j += NT) active[j] = j;
 
     // gap-safe screening (sklearn _cd_fast.pyx:1187-1208, :1259-1279).  Ordered compaction
     // of the surviving coordinates; dropped non-zero coordinates are applied afterwards in
@@ -195,11 +203,11 @@ enet_cd_gram_kernel(const double *const *__restrict__ prob_Q, const double *cons
             int j = -1, keep = 0;
             if (idx < n_cand) {
                 j = initial ? idx : active[idx];
-                const double djj = ds[j];
+                const double djj = __ldg(dg + j);
                 if (initial && djj == 0.0) {
                     w[j] = 0.0;
                 } else {
-                    const double xta = qs[j] - Qw[j] - l2 * w[j];
+                    const double xta = __ldg(q + j) - Qw[j] - l2 * w[j];
                     const double d_j = (1.0 - fabs(xta / denom)) / sqrt(djj + l2);
                     if (d_j <= radius) keep = 1;
                     else if (w[j] != 0.0) { state[j] = 2; any_drop = 1; }
@@ -245,40 +253,142 @@ enet_cd_gram_kernel(const double *const *__restrict__ prob_Q, const double *cons
     bool done = (gap >= 0.0 && gap <= tol) || max_iter <= 0;
     if (!done) {
         if (screening) screen(gap, true);
+        cta_sync<NW>();
         for (n_iter = 0; n_iter < max_iter; ++n_iter) {
-            double w_max = 0.0, d_w_max = 0.0;
-            for (int f = 0; f < n_active; ++f) {
-                const int j = screening ? active[f] : f;
-                const double djj = ds[j];
-                if (djj == 0.0) continue;
-                const double w_j = w[j];
-                const double tmp = qs[j] - Qw[j] + w_j * djj;
-                const double w_new = copysign(fmax(fabs(tmp) - l1, 0.0), tmp) / (djj + l2);
-                if (w_new != w_j) {
-                    cta_sync<NW>();           // every thread has read w[j], Qw[j]
-                    axpy_row(j, w_new - w_j);
-                    if (tid == 0) w[j] = w_new;
-                    ++n_upd;
-                    cta_sync<NW>();
+            double wmax_l = 0.0, dwmax_l = 0.0;            // per-lane maxima (warp 0)
+            const int n_blocks = (n_active + 31) >> 5;
+            // block registers of warp 0: coordinate, q, diag, 1/(diag+l2), column of the diagonal sub-block
+            int j_l = 0;
+            bool ok_l = false, valid_l = false;
+            double q_l = 0.0, d_l = 0.0, inv_l = 0.0, den_l = 1.0;
+            double col[32];
+            auto load_block = [&](int b) {
+                const int pos = (b << 5) + lane;
+                valid_l = pos < n_active;
+                j_l = valid_l ? active[pos] : 0;
+                q_l = valid_l ? __ldg(q + j_l) : 0.0;
+                d_l = valid_l ? __ldg(dg + j_l) : 0.0;
+                ok_l = valid_l && d_l != 0.0;
+                den_l = ok_l ? d_l + l2 : 1.0;
+                inv_l = 1.0 / den_l;
+                const int nb = min(32, n_active - (b << 5));
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int ji = (i < nb) ? active[(b << 5) + i] : 0;          // smem broadcast
+                    col[i] = (i < nb && valid_l) ? __ldg(Q + (long long)ji * ldq + j_l) : 0.0;
                 }
-                d_w_max = fmax(d_w_max, fabs(w_new - w_j));
-                w_max = fmax(w_max, fabs(w_new));
-            }
-            if (w_max == 0.0 || d_w_max / w_max <= d_w_tol || n_iter == max_iter - 1) {
+            };
+            if (warp == 0 && n_blocks > 0) load_block(0);
+
+            for (int b = 0; b < n_blocks; ++b) {
+                if (warp == 0) {
+                    // ---------------- phase 1: the 32 coordinates of the block, in order
+                    double Qw_l = valid_l ? Qw[j_l] : 0.0;
+                    const double w_l = valid_l ? w[j_l] : 0.0;
+                    const double wd_l = w_l * d_l;
+                    double w_new_l = w_l, delta_l = 0.0;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const double tmp = (q_l - Qw_l) + wd_l;
+                        const double soft = copysign(fmax(fabs(tmp) - l1, 0.0), tmp);
+                        double cand = soft * inv_l;
+                        cand = fma(fma(-den_l, cand, soft), inv_l, cand);     // one Newton step: soft / den
+                        const double dc = ok_l ? cand - w_l : 0.0;
+                        const double di = __shfl_sync(0xffffffffu, dc, i);
+                        if (lane == i) { w_new_l = ok_l ? cand : w_l; delta_l = dc; }
+                        Qw_l = fma(di, col[i], Qw_l);
+                    }
+                    const unsigned nz = __ballot_sync(0xffffffffu, delta_l != 0.0);
+                    if (ok_l) {
+                        dwmax_l = fmax(dwmax_l, fabs(delta_l));
+                        wmax_l = fmax(wmax_l, fabs(w_new_l));
+                    }
+                    if (delta_l != 0.0) {
+                        w[j_l] = w_new_l;
+                        const int slot = __popc(nz & ((1u << lane) - 1));          // compacted, block order
+                        dlt[slot] = delta_l;
+                        jb[slot] = j_l;
+                    }
+                    if (lane == 0) iscr[NW + 1] = __popc(nz);
+                    n_upd += __popc(nz);
+                    ++n_blk;
+                    if (b + 1 < n_blocks) load_block(b + 1);      // in flight during phase 2
+                }
                 cta_sync<NW>();
+                // ---------------- phase 2: Qw += sum_i delta_i Q[j_i, :]   (rows in block order)
+                const int n_rows = iscr[NW + 1];
+                if (n_rows > 0 && warp > 0) {
+                    const int bt = tid - 32;
+                    if (vec2) {
+                        const double2 *Q2 = reinterpret_cast<const double2 *>(Q);
+                        double2 *Qw2 = reinterpret_cast<double2 *>(Qw);
+                        const long long ld2 = ldq >> 1;
+                        for (int c0 = bt; c0 < Cp2; c0 += NTB * CD_CH) {
+                            double2 acc[CD_CH];
+#pragma unroll
+                            for (int u = 0; u < CD_CH; ++u) {
+                                const int c = c0 + u * NTB;
+                                acc[u] = (c < Cp2) ? Qw2[c] : make_double2(0.0, 0.0);
+                            }
+                            for (int r0 = 0; r0 < n_rows; r0 += CD_RG) {
+                                double2 v[CD_RG][CD_CH];
+                                double dl[CD_RG];
+#pragma unroll
+                                for (int rr = 0; rr < CD_RG; ++rr) {
+                                    const bool rok = r0 + rr < n_rows;
+                                    dl[rr] = rok ? dlt[r0 + rr] : 0.0;
+                                    const double2 *row = Q2 + (long long)jb[rok ? r0 + rr : r0] * ld2;
+#pragma unroll
+                                    for (int u = 0; u < CD_CH; ++u) {
+                                        const int c = c0 + u * NTB;
+                                        v[rr][u] = (c < Cp2) ? __ldg(row + c) : make_double2(0.0, 0.0);
+                                    }
+                                }
+#pragma unroll
+                                for (int rr = 0; rr < CD_RG; ++rr)
+#pragma unroll
+                                    for (int u = 0; u < CD_CH; ++u) {
+                                        acc[u].x = fma(dl[rr], v[rr][u].x, acc[u].x);
+                                        acc[u].y = fma(dl[rr], v[rr][u].y, acc[u].y);
+                                    }
+                            }
+#pragma unroll
+                            for (int u = 0; u < CD_CH; ++u) {
+                                const int c = c0 + u * NTB;
+                                if (c < Cp2) Qw2[c] = acc[u];
+                            }
+                        }
+                    } else {
+                        for (int k = bt; k < C; k += NTB) {
+                            double a = Qw[k];
+                            for (int r = 0; r < n_rows; ++r) a = fma(dlt[r], __ldg(Q + (long long)jb[r] * ldq + k), a);
+                            Qw[k] = a;
+                        }
+                    }
+                }
+                cta_sync<NW>();
+            }
+            // sweep maxima (uniform in all threads)
+            double mx[2] = {warp == 0 ? wmax_l : 0.0, warp == 0 ? dwmax_l : 0.0};
+            cta_reduce<NW, 2, 0>(mx, scratch);
+            const double w_max = mx[0], d_w_max = mx[1];
+            if (w_max == 0.0 || d_w_max / w_max <= d_w_tol || n_iter == max_iter - 1) {
                 gap = compute_gap();
                 if (gap <= tol) { ++n_iter; done = true; break; }
                 if (screening) screen(gap, false);
+                cta_sync<NW>();
             }
         }
     }
     cta_sync<NW>();
     for (int j = tid; j < C; j += NT) W[(long long)m * ldw + j] = w[j];
     if (tid == 0) {
-        info[4 * m + 0] = gap;
-        info[4 * m + 1] = tol;
-        info[4 * m + 2] = (double)n_iter;
-        info[4 * m + 3] = (double)n_upd;
+        info[6 * m + 0] = gap;
+        info[6 * m + 1] = tol;
+        info[6 * m + 2] = (double)n_iter;
+        info[6 * m + 3] = (double)n_upd;
+        info[6 * m + 4] = (double)n_upd + (double)n_blk * (32.0 * 32.0) / (double)C;   // rows fetched (equiv.)
+        info[6 * m + 5] = (double)n_blk;
     }
 }
 
@@ -520,50 +630,54 @@ using namespace sglm;
 
 extern "C" int sglm_center_stats_f64(const double *A_plus, const double *A_minus, int64_t ldg, int32_t C,
                                      int32_t n_y, int32_t y_col, int32_t fit_intercept, double *Qc,
-                                     int64_t ldq, double *qc, double *xbar, double *scal, void *stream) {
+                                     int64_t ldq, double *qc, double *xbar, double *diag, double *scal,
+                                     void *stream) {
     SGLM_CHECK_ARG(C > 0 && n_y > 0 && y_col >= 0 && y_col < n_y, SGLM_E_SHAPE, "center_stats: bad shape");
-    SGLM_CHECK_ARG(A_plus && Qc && qc && xbar && scal, SGLM_E_INVALID_ARG, "center_stats: null pointer");
+    SGLM_CHECK_ARG(A_plus && Qc && qc && xbar && diag && scal, SGLM_E_INVALID_ARG, "center_stats: null pointer");
     SGLM_CHECK_ARG(ldg >= C + n_y + 1 && ldq >= C, SGLM_E_SHAPE, "center_stats: leading dimension too small");
     dim3 grid((unsigned)std::min<long long>(ceil_div<long long>(ldq, 256), 64), (unsigned)C);
     center_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A_plus, A_minus, ldg, C, n_y, y_col,
-                                                                 fit_intercept, Qc, ldq, qc, xbar, scal);
+                                                                 fit_intercept, Qc, ldq, qc, xbar, diag, scal);
     SGLM_LAUNCH_OK("center_stats_kernel");
     return SGLM_OK;
 }
 
 static size_t cd_smem_bytes(int C, int nw) {
     const int Cp = (C + 1) & ~1;
-    return (size_t)(4 * Cp + nw * 8) * sizeof(double) + (size_t)(C + nw + 1) * sizeof(int) + (size_t)C;
+    return (size_t)(2 * Cp + nw * 8 + 32) * sizeof(double) + (size_t)(C + 32 + nw + 2) * sizeof(int) + (size_t)C;
 }
 
 extern "C" int sglm_enet_cd_gram_f64(const double *const *prob_Q, const double *const *prob_q,
-                                     const double *prob_yy, int64_t ldq, int32_t C,
+                                     const double *const *prob_diag, const double *prob_yy, int64_t ldq, int32_t C,
                                      const int32_t *prob_of_model, const double *l1_reg,
                                      const double *l2_reg, const double *tol, const int32_t *max_iter,
                                      int32_t n_models, int32_t warm_start, int32_t do_screening,
                                      double *W, int64_t ldw, double *info, void *stream) {
     SGLM_CHECK_ARG(C > 0 && n_models >= 0 && ldq >= C && ldw >= C, SGLM_E_SHAPE, "enet_cd: bad shape");
     if (n_models == 0) return SGLM_OK;
-    SGLM_CHECK_ARG(prob_Q && prob_q && prob_yy && prob_of_model && l1_reg && l2_reg && tol && max_iter && W && info,
+    SGLM_CHECK_ARG(prob_Q && prob_q && prob_diag && prob_yy && prob_of_model && l1_reg && l2_reg && tol && max_iter && W && info,
                    SGLM_E_INVALID_ARG, "enet_cd: null pointer");
-    const int nw = C <= 384 ? 1 : (C <= 768 ? 2 : (C <= 2048 ? 4 : 8));
+    const int nb = C <= 256 ? 1 : (C <= 512 ? 2 : (C <= 1024 ? 4 : 8));   // panel-update warps (+1 sequential warp)
+    const int nw = nb + 1;
     const size_t smem = cd_smem_bytes(C, nw);
     SGLM_CHECK_ARG(smem <= 227 * 1024, SGLM_E_UNSUPPORTED,
                    "enet_cd: C=%d needs %zu bytes of shared memory per model (> 227 KB)", C, smem);
     cudaStream_t st = (cudaStream_t)stream;
-#define CD_LAUNCH(N)                                                                                       \
+#define CD_LAUNCH(N, RG, MB)                                                                               \
     do {                                                                                                   \
-        SGLM_CUDA_OK(cudaFuncSetAttribute(enet_cd_gram_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          (int)smem));                                                     \
-        enet_cd_gram_kernel<N><<<n_models, N * 32, smem, st>>>(prob_Q, prob_q, prob_yy, ldq, C, prob_of_model, \
-                                                              l1_reg, l2_reg, tol, max_iter, warm_start,  \
-                                                              do_screening, W, ldw, info);                 \
+        SGLM_CUDA_OK(cudaFuncSetAttribute(enet_cd_gram_kernel<N, RG, MB>,                                  \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+        enet_cd_gram_kernel<N, RG, MB><<<n_models, (N + 1) * 32, smem, st>>>(                              \
+            prob_Q, prob_q, prob_diag, prob_yy, ldq, C, prob_of_model, l1_reg, l2_reg, tol, max_iter,      \
+            warm_start, do_screening, W, ldw, info);                                                       \
     } while (0)
-    switch (nw) {
-        case 1: CD_LAUNCH(1); break;
-        case 2: CD_LAUNCH(2); break;
-        case 4: CD_LAUNCH(4); break;
-        default: CD_LAUNCH(8); break;
+    // (panel warps, rows per group, min CTAs/SM) tuned on B200: the variants without register
+    // spills win; for C in (1024, 2048] one 9-warp CTA per SM (profiles/r1_cd_variants.txt)
+    switch (nb) {
+        case 1: CD_LAUNCH(1, 4, 4); break;
+        case 2: CD_LAUNCH(2, 4, 4); break;
+        case 4: CD_LAUNCH(4, 4, 2); break;
+        default: CD_LAUNCH(8, 4, 1); break;
     }
 #undef CD_LAUNCH
     SGLM_LAUNCH_OK("enet_cd_gram_kernel");
