@@ -284,6 +284,7 @@ def main():
             peaks_src = "measured"
     except Exception:
         pass
+    tc_plan = nat.last_tc_plan
     n_rows = args.T - h_lo - h_hi
     n_test = sum(len(b) for _, b in folds_h)
     n_aug = C + 2
@@ -295,6 +296,7 @@ def main():
     alg = {
         "sglm_timeshift_f64_ranged": ("hbm", 8.0 * args.T * args.P + 8.0 * args.T * C),
         "sglm_suffstats_f64": ("tensor", float(n_rows + n_test) * (n_aug * (n_aug + 1.0))),
+        "sglm_gram_tc_f64": ("tensor", float(n_rows + n_test) * (n_aug * (n_aug + 1.0))),
         "sglm_enet_cd_gram_f64": ("hbm", n_upd * 8.0 * C + n_sweeps * 8.0 * 5 * C),
         "sglm_quadform_f64": ("hbm", 0.0),
     }
@@ -311,6 +313,9 @@ def main():
                 "other": {
                     "gather_GBps": alg["sglm_timeshift_f64_ranged"][1] / (k_ms.get("sglm_timeshift_f64_ranged", np.inf) / 1e3) / 1e9,
                     "suffstats_fp64_TFLOPs_syrk_honest": alg["sglm_suffstats_f64"][1] / (k_ms.get("sglm_suffstats_f64", np.inf) / 1e3) / 1e12,
+                    "gram_tc_useful_TFLOPs_syrk_honest": alg["sglm_gram_tc_f64"][1] / (k_ms.get("sglm_gram_tc_f64", np.inf) / 1e3) / 1e12,
+                    "gram_tc_issued_int8_TOPs": (2.0 * tc_plan["tiles"] * 128 * 256 * tc_plan["n_pos"] / (k_ms.get("sglm_gram_tc_f64", np.inf) / 1e3) / 1e12) if tc_plan else None,
+                    "gram_tc_plan": tc_plan,
                     "cd_GBps": alg["sglm_enet_cd_gram_f64"][1] / (k_ms.get("sglm_enet_cd_gram_f64", np.inf) / 1e3) / 1e9,
                     "cd_row_updates_per_step": n_upd,
                     "cd_sweeps_total": n_sweeps, "models_not_converged": n_unconv}}

@@ -92,6 +92,34 @@ int sglm_suffstats_f64(const double *X, int64_t ldx, const double *Y, int64_t ld
                        const int32_t *ksplit_host, double *G, int64_t ldg, void *workspace,
                        size_t workspace_bytes, void *stream);
 
+/* ------------------------------------------------------------------------- *
+ * Tensor-core Gram (tcgen05 kind::i8 + TMA + TMEM): the same statistics as
+ * sglm_suffstats_f64 for 0/1 row sets, computed exactly in integers from signed
+ * radix-128 digit planes of the fp64 columns (split / Ozaki scheme) and recombined in
+ * fp64; columns that are exactly representable in fewer digits (0/1 event indicators)
+ * only get the planes they need.  Two calls:
+ *   analyze : device colE[n_aug] (scale exponents), colS[n_aug] (digit planes per column,
+ *             1..8), flag != 0 when the data hold NaN/inf.  colmax_scratch: n_aug uint64.
+ *   gram    : colS_host = host copy of colS; set_rows_host[s] = rows of set s; rows = device
+ *             int64, the concatenated row lists of the sets, each padded with -1 to a multiple
+ *             of 128.  G as in sglm_suffstats_f64.  use_check_gemm != 0 replaces the tcgen05
+ *             GEMM by a CUDA-core integer GEMM (bit-identical results; validation only).
+ *   plan_info: out4_host = {digit-plane rows S, positions, output tiles of 128x256, K segments}
+ *             (issued int8 MACs = tiles * 128 * 256 * positions).
+ * ------------------------------------------------------------------------- */
+int sglm_gram_tc_analyze_f64(const double *X, int64_t ldx, const double *Y, int64_t ldy, int32_t n_y,
+                             int64_t T, int32_t C, int32_t *colE, int32_t *colS,
+                             uint64_t *colmax_scratch, int32_t *flag, void *stream);
+size_t sglm_gram_tc_workspace_bytes(int32_t n_aug, const int32_t *colS_host, int32_t n_sets,
+                                    const int64_t *set_rows_host);
+int sglm_gram_tc_plan_info(int32_t n_aug, const int32_t *colS_host, int32_t n_sets,
+                           const int64_t *set_rows_host, int64_t *out4_host);
+int sglm_gram_tc_f64(const double *X, int64_t ldx, const double *Y, int64_t ldy, int32_t n_y, int64_t T,
+                     int32_t C, const int32_t *colE, const int32_t *colS, const int32_t *colS_host,
+                     int32_t n_sets, const int64_t *set_rows_host, const int64_t *rows, double *G,
+                     int64_t ldg, void *workspace, size_t workspace_bytes, int32_t use_check_gemm,
+                     void *stream);
+
 /* Index lists -> per-row multiplicities: counts[idx[i]] += 1 (the fold row sets of
  * backend/sglm_cv.py:106-110, X[idx_train,:] / X[idx_test,:]).  counts must be zeroed. */
 int sglm_index_counts_f64(const int64_t *idx, int64_t n_idx, double *counts, int64_t T,

@@ -171,6 +171,56 @@ def suffstats(Xd, Yd, W=None, rows_hint=None):
     return G
 
 
+def suffstats_tc(Xd, Yd, set_rows, check_gemm=False):
+    """Tensor-core Gram (tcgen05 int8 digit planes, exact integer accumulation, fp64
+    recombination): same output as `suffstats` for 0/1 row sets.
+    set_rows: list with one entry per set — None (all rows) or a sorted, duplicate-free int64
+    CUDA tensor of row indices.  Returns G [n_sets, n_aug, ldg]."""
+    torch = nat.require_cuda()
+    T, C = Xd.shape
+    n_y = Yd.shape[1]
+    n_aug = C + n_y + 1
+    n_sets = len(set_rows)
+    ldg = _round_up(n_aug, 8)
+    colE = torch.empty(n_aug, dtype=torch.int32, device="cuda")
+    colS = torch.empty(n_aug, dtype=torch.int32, device="cuda")
+    scratch = torch.empty(n_aug, dtype=torch.int64, device="cuda")
+    flag = torch.empty(1, dtype=torch.int32, device="cuda")
+    call("sglm_gram_tc_analyze_f64", ptr(Xd), row_stride(Xd), ptr(Yd), row_stride(Yd), n_y, T, C, ptr(colE),
+         ptr(colS), ptr(scratch), ptr(flag), stream_ptr())
+    host = torch.cat([colS, flag]).cpu().numpy()
+    if host[-1] != 0:
+        raise ValueError("Input contains NaN, infinity or a value too large for dtype('float64').")
+    colS_h = np.ascontiguousarray(host[:-1], dtype=np.int32)
+    sizes = np.ascontiguousarray([T if r is None else int(r.numel()) for r in set_rows], dtype=np.int64)
+    parts = []
+    for r, n in zip(set_rows, sizes):
+        body = torch.arange(T, dtype=torch.int64, device="cuda") if r is None else r.to(torch.int64)
+        pad = (-int(n)) % 128
+        parts.append(body)
+        if pad:
+            parts.append(torch.full((pad,), -1, dtype=torch.int64, device="cuda"))
+    rows = torch.cat(parts) if parts else torch.empty(0, dtype=torch.int64, device="cuda")
+    if rows.numel() == 0:
+        rows = torch.full((128,), -1, dtype=torch.int64, device="cuda")
+    ws_bytes = nat.lib().sglm_gram_tc_workspace_bytes(n_aug, colS_h.ctypes.data_as(ctypes.c_void_p), n_sets,
+                                                      sizes.ctypes.data_as(ctypes.c_void_p))
+    if ws_bytes == 0:
+        raise nat.SglmNativeError("gram_tc: invalid plan")
+    info = np.zeros(4, dtype=np.int64)
+    nat.lib().sglm_gram_tc_plan_info(n_aug, colS_h.ctypes.data_as(ctypes.c_void_p), n_sets,
+                                     sizes.ctypes.data_as(ctypes.c_void_p), info.ctypes.data_as(ctypes.c_void_p))
+    nat.last_tc_plan = dict(S=int(info[0]), n_pos=int(info[1]), tiles=int(info[2]), segs=int(info[3]),
+                            planes=int(colS_h.sum()), n_aug=n_aug)
+    raw = torch.empty(ws_bytes + 1024, dtype=torch.uint8, device="cuda")
+    off = (-raw.data_ptr()) % 1024
+    G = _zeros((n_sets, n_aug, ldg))
+    call("sglm_gram_tc_f64", ptr(Xd), row_stride(Xd), ptr(Yd), row_stride(Yd), n_y, T, C, ptr(colE), ptr(colS),
+         colS_h.ctypes.data_as(ctypes.c_void_p), n_sets, sizes.ctypes.data_as(ctypes.c_void_p), ptr(rows), ptr(G), ldg,
+         ctypes.c_void_p(raw.data_ptr() + off), ws_bytes, int(bool(check_gemm)), stream_ptr())
+    return G, colS_h
+
+
 class Problem:
     """Centred problem (Qc, qc, yyc, xbar, ybar, n) of one (row set, y column, intercept)."""
     __slots__ = ("Qc", "qc", "xbar", "diag", "scal", "ldq", "fit_intercept", "y_col", "n", "ybar", "yyc", "sy")

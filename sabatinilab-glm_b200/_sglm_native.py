@@ -27,6 +27,11 @@ _PROTOTYPES = {
     "sglm_suffstats_workspace_bytes": (c_sz, [c_i64, c_i32, c_i32, c_i32, c_vp]),
     "sglm_suffstats_f64": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_i64, c_i32,
                                    c_vp, c_vp, c_i64, c_vp, c_sz, c_vp]),
+    "sglm_gram_tc_analyze_f64": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "sglm_gram_tc_workspace_bytes": (c_sz, [c_i32, c_vp, c_i32, c_vp]),
+    "sglm_gram_tc_plan_info": (c_i32, [c_i32, c_vp, c_i32, c_vp, c_vp]),
+    "sglm_gram_tc_f64": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp,
+                                 c_vp, c_vp, c_i64, c_vp, c_sz, c_i32, c_vp]),
     "sglm_index_counts_f64": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp]),
     "sglm_center_stats_f64": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64,
                                       c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -97,7 +102,7 @@ def ptr(t):
 
 
 # kernels launched per ABI call (for the launch count bench.py reports)
-_KERNELS_PER_CALL = {"sglm_suffstats_f64": 3, "sglm_score_f64": 2, "sglm_poisson_irls_prepare_f64": 2,
+_KERNELS_PER_CALL = {"sglm_suffstats_f64": 3, "sglm_gram_tc_analyze_f64": 3, "sglm_gram_tc_f64": 3, "sglm_score_f64": 2, "sglm_poisson_irls_prepare_f64": 2,
                      "sglm_timeshift_f64": 2}
 _timing = None         # when enabled: list of (name, start_event, end_event) on the current stream
 
@@ -120,6 +125,9 @@ def collect_timing():
             out[name] = (c + 1, t + e0.elapsed_time(e1))
         _timing = []
     return out
+
+
+last_tc_plan = None     # {S, n_pos, tiles, segs} of the most recent tensor-core Gram (bench.py reads it)
 
 
 def call(name, *args):

@@ -1,0 +1,612 @@
+// Tensor-core Gram builder: fp64-grade  G = Z' Z  (Z = [X | Y | 1], several row sets) on the
+// 5th-generation tensor cores — tcgen05.mma kind::i8 with int32 accumulators in TMEM, operands
+// staged by TMA into 128B-swizzled shared memory, mbarrier producer/consumer pipeline.
+//
+// tcgen05 has no f64 kind, so the fp64 Gram is computed EXACTLY in integers (split / Ozaki
+// scheme): every column c of Z is scaled by 2^-E_c (E_c from the column's max |z|) and cut into
+// signed radix-128 digits  z = 2^E_c (d_1 2^-6 + d_2 2^-13 + ... + d_s 2^-(6+7(s-1))),
+// |d_k| <= 64, which int8 holds exactly.  The Gram of two digit planes is an int8 x int8 -> int32
+// GEMM whose result is exact (|d d'| <= 2^12, drained from TMEM before 2^31 can be reached) and
+// is accumulated in int64; the fp64 Gram is the power-of-two weighted sum of the digit-plane
+// Grams.  With s = 8 planes the representation error is 2^-56 of the column scale — fp64 grade —
+// and a column whose values are exactly representable in fewer digits (the 0/1 event indicators
+// that make up most of a photometry design need ONE plane) is detected and only gets the planes
+// it needs, so the integer work adapts to the data: ~4 dense int8 GEMM equivalents for the c3
+// workload instead of 36.
+//
+// Replaces the same reference arithmetic as suffstats.cu (the X'X / X'y of every sklearn fit,
+// backend/sglm.py:241) and produces the same output contract as sglm_suffstats_f64 for 0/1 row
+// sets; the DMMA kernel remains the path for general row weights (Poisson IRLS) and the on-GPU
+// cross-check of this one.
+//
+// Pipeline:  colscale -> digit count -> slice (digits, transposed to K-major, rows gathered per
+// set) -> int8 tcgen05 GEMM over digit-plane tile pairs -> combine (fp64).
+#include <cuda.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace sglm {
+
+constexpr int TC_SMAX = 8;       // digit planes for a general fp64 column
+constexpr int TC_BK = 128;       // K bytes (= int8 elements = design rows) per pipeline stage
+constexpr int TC_BM = 128;       // UMMA M
+constexpr int TC_BN = 256;       // UMMA N
+constexpr int TC_STAGES = 4;
+constexpr int TC_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int TC_MAX_KB_PER_SEG = 2048;   // 2048 * 128 rows * 2^12 < 2^31
+constexpr uint32_t TC_STAGE_BYTES = (TC_BM + TC_BN) * TC_BK;
+
+// ------------------------------------------------------------------ column scale and digit count
+__device__ __forceinline__ double z_value(const double *X, long long ldx, const double *Y, long long ldy,
+                                          int C, int n_y, long long t, int c) {
+    if (c < C) return X[t * ldx + c];
+    if (c < C + n_y) return Y[t * ldy + (c - C)];
+    return 1.0;
+}
+
+__global__ void __launch_bounds__(256)
+tc_colmax_kernel(const double *__restrict__ X, long long ldx, const double *__restrict__ Y, long long ldy,
+                 int C, int n_y, long long T, unsigned long long *__restrict__ colmax_bits) {
+    const int n_aug = C + n_y + 1;
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= n_aug) return;
+    const long long rows_per = (T + gridDim.y - 1) / gridDim.y;
+    const long long t0 = (long long)blockIdx.y * rows_per, t1 = min(T, t0 + rows_per);
+    double m = 0.0;
+    bool bad = false;
+    for (long long t = t0; t < t1; ++t) {
+        const double v = fabs(z_value(X, ldx, Y, ldy, C, n_y, t, c));
+        bad |= !(v <= 1.7976931348623157e308);          // NaN or inf
+        m = fmax(m, v);
+    }
+    if (bad) m = __longlong_as_double(0x7ff8000000000000LL);
+    atomicMax(colmax_bits + c, (unsigned long long)__double_as_longlong(m));   // monotone for non-negative doubles; NaN pattern wins
+}
+
+// number of radix digits (1..TC_SMAX) a value needs to be represented exactly at scale 2^E
+__device__ __forceinline__ int digits_needed(double z, int E) {
+    double r = scalbn(z, -E);            // |r| < 1
+    int need = 0;
+    r *= 64.0;
+#pragma unroll
+    for (int k = 1; k <= TC_SMAX; ++k) {
+        if (r == 0.0) break;
+        const double d = rint(r);
+        if (d != 0.0) need = k;
+        r = (r - d) * 128.0;
+    }
+    if (r != 0.0) need = TC_SMAX;
+    return need;
+}
+
+__global__ void __launch_bounds__(256)
+tc_digits_kernel(const double *__restrict__ X, long long ldx, const double *__restrict__ Y, long long ldy,
+                 int C, int n_y, long long T, const int *__restrict__ colE, int *__restrict__ colS) {
+    const int n_aug = C + n_y + 1;
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= n_aug) return;
+    const long long rows_per = (T + gridDim.y - 1) / gridDim.y;
+    const long long t0 = (long long)blockIdx.y * rows_per, t1 = min(T, t0 + rows_per);
+    const int E = colE[c];
+    int need = 1;
+    for (long long t = t0; t < t1 && need < TC_SMAX; ++t)
+        need = max(need, digits_needed(z_value(X, ldx, Y, ldy, C, n_y, t, c), E));
+    atomicMax(colS + c, need);
+}
+
+__global__ void tc_exponent_kernel(const unsigned long long *__restrict__ colmax_bits, int n_aug,
+                                   int *__restrict__ colE, int *__restrict__ colS, int *__restrict__ flag) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_aug) return;
+    const double m = __longlong_as_double((long long)colmax_bits[c]);
+    if (!(m <= 1.7976931348623157e308)) { atomicOr(flag, 1); colE[c] = 0; colS[c] = 1; return; }
+    colE[c] = (m == 0.0) ? 0 : ilogb(m) + 1;      // |z| < 2^E
+    colS[c] = 1;
+}
+
+// ------------------------------------------------------------------ slicing (digits, transposed, gathered rows)
+// At[(plane k of column c)][p] = digit k of Z[rows[p], c];  p runs over the concatenated, 128-padded
+// row lists of all sets (rows[p] < 0 marks padding -> zeros, which the buffer already holds).
+__global__ void __launch_bounds__(256)
+tc_slice_kernel(const double *__restrict__ X, long long ldx, const double *__restrict__ Y, long long ldy,
+                int C, int n_y, const long long *__restrict__ rows, long long n_pos,
+                const int *__restrict__ colE, const int *__restrict__ colS, const int *__restrict__ plane_row,
+                int8_t *__restrict__ At, long long ld_at) {
+    // plane_row[c * TC_SMAX + (k-1)] = row of At holding digit plane k of column c (or -1)
+    __shared__ double tile[128][33];
+    const int n_aug = C + n_y + 1;
+    const long long p0 = (long long)blockIdx.x * 128;
+    const int c0 = blockIdx.y * 32;
+    const int tid = threadIdx.x;
+    // load 128 positions x 32 columns, coalesced along the columns of the row-major source
+    for (int i = tid; i < 128 * 32; i += 256) {
+        const int r = i >> 5, cc = i & 31;
+        const long long p = p0 + r;
+        const int c = c0 + cc;
+        double v = 0.0;
+        if (p < n_pos && c < n_aug) {
+            const long long t = rows[p];
+            if (t >= 0) v = z_value(X, ldx, Y, ldy, C, n_y, t, c);
+        }
+        tile[r][cc] = v;
+    }
+    __syncthreads();
+    // thread <-> (position, 16 columns); lanes run along the positions -> 32-byte coalesced digit stores
+    const int r = tid & 127, half = tid >> 7;
+    const long long p = p0 + r;
+    if (p >= n_pos) return;
+    for (int cc = half * 16; cc < half * 16 + 16; ++cc) {
+        const int c = c0 + cc;
+        if (c >= n_aug) break;
+        const int S = colS[c];
+        double rr = scalbn(tile[r][cc], -colE[c]) * 64.0;
+        for (int k = 1; k <= S; ++k) {
+            const double d = rint(rr);
+            rr = (rr - d) * 128.0;
+            At[(long long)plane_row[c * TC_SMAX + (k - 1)] * ld_at + p] = (int8_t)(int)d;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ PTX helpers (mbarrier / TMA / tcgen05)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a protocol bug must surface as a trapped kernel, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    const long long t_start = clock64();
+    while (true) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (clock64() - t_start > 4000000000LL) { asm volatile("trap;"); }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tmap, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major, 128B-swizzled operand tile (rows of 128 bytes, 8-row groups 1024 bytes apart): the
+// layout TMA writes for CU_TENSOR_MAP_SWIZZLE_128B with a 128-byte inner box.
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);          // start address
+    d |= (uint64_t)1 << 16;                               // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset: next 8-row group
+    d |= (uint64_t)1 << 46;                               // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                               // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: dense, S32 accumulate, A/B signed int8, both K-major, M=128, N=256
+__host__ __device__ constexpr uint32_t tc_idesc_i8() {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+struct TcSeg { int kb0, n_kb, set, first; };
+
+// ------------------------------------------------------------------ the int8 tcgen05 GEMM
+// One CTA per output tile (128 x 256 of the digit-plane Gram); K runs over the row segments of all
+// sets; each segment's int32 accumulator is drained from TMEM into the int64 tile of its set.
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gram_i8_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restrict__ tiles,
+                  const TcSeg *__restrict__ segs, int n_segs, long long *__restrict__ SG, long long S) {
+    extern __shared__ __align__(1024) uint8_t tc_smem[];
+    uint8_t *base = (uint8_t *)(((uintptr_t)tc_smem + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = base;                                           // [STAGES][128][128]
+    uint8_t *sB = base + TC_STAGES * TC_BM * TC_BK;               // [STAGES][256][128]
+    uint64_t *bars = (uint64_t *)(base + TC_STAGES * TC_STAGE_BYTES);
+    uint64_t *full = bars, *empty = bars + TC_STAGES, *tmem_full = bars + 2 * TC_STAGES, *tmem_empty = tmem_full + 1;
+    uint32_t *tmem_slot = (uint32_t *)(tmem_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int2 tile = tiles[blockIdx.x];
+    const int m0 = tile.x * TC_BM, n0 = tile.y * TC_BN;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (one elected lane)
+        if (lane == 0) {
+            int it = 0;
+            for (int sgi = 0; sgi < n_segs; ++sgi) {
+                const TcSeg sg = segs[sgi];
+                for (int kb = 0; kb < sg.n_kb; ++kb, ++it) {
+                    const int st = it % TC_STAGES;
+                    const uint32_t ph = (it / TC_STAGES) & 1;
+                    mbar_wait(empty + st, ph ^ 1);
+                    mbar_expect_tx(full + st, TC_STAGE_BYTES);
+                    const int kc = (sg.kb0 + kb) * TC_BK;
+                    tma_load_2d(sA + st * TC_BM * TC_BK, &tmap, full + st, kc, m0);
+                    tma_load_2d(sB + st * TC_BN * TC_BK, &tmap, full + st, kc, n0);
+                    tma_load_2d(sB + st * TC_BN * TC_BK + 128 * TC_BK, &tmap, full + st, kc, n0 + 128);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one elected lane)
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc_idesc_i8();
+            int it = 0;
+            for (int sgi = 0; sgi < n_segs; ++sgi) {
+                const TcSeg sg = segs[sgi];
+                if (sgi > 0) { mbar_wait(tmem_empty, (sgi - 1) & 1); tc_fence_after(); }
+                for (int kb = 0; kb < sg.n_kb; ++kb, ++it) {
+                    const int st = it % TC_STAGES;
+                    const uint32_t ph = (it / TC_STAGES) & 1;
+                    mbar_wait(full + st, ph);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_k_sw128(smem_u32(sA + st * TC_BM * TC_BK));
+                    const uint64_t db = umma_desc_k_sw128(smem_u32(sB + st * TC_BN * TC_BK));
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 32; ++k)          // UMMA K = 32 int8: +32 bytes inside the swizzle atom
+                        tc_mma_i8(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                    tc_commit(empty + st);                         // frees the stage when these MMAs retire
+                }
+                tc_commit(tmem_full);                              // accumulator of this segment complete
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> int64 tile of the segment's set (sole owner, no atomics)
+        const int q = warp & 3;                                    // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        for (int sgi = 0; sgi < n_segs; ++sgi) {
+            const TcSeg sg = segs[sgi];
+            mbar_wait(tmem_full, sgi & 1);
+            tc_fence_after();
+            long long *out = SG + ((long long)sg.set * S + (m0 + row)) * S + n0;
+#pragma unroll 1
+            for (int ch = 0; ch < TC_BN / 32; ++ch) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (sg.n_kb == 0) {                              // empty row set: nothing was accumulated
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 0u;
+                }
+                long long *o = out + ch * 32;
+                if (sg.first) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) o[j] = (long long)(int)v[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) o[j] += (long long)(int)v[j];
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(256));
+    }
+}
+
+// Plain-CUDA-core version of the same tile computation (validation of the tcgen05 path on the
+// GPU itself: the integer results must be identical).  One thread per output element.
+__global__ void __launch_bounds__(256)
+tc_gram_i8_check_kernel(const int8_t *__restrict__ At, long long ld_at, const int2 *__restrict__ tiles,
+                        const TcSeg *__restrict__ segs, int n_segs, long long *__restrict__ SG, long long S) {
+    const int2 tile = tiles[blockIdx.x];
+    const int m0 = tile.x * TC_BM, n0 = tile.y * TC_BN;
+    for (int e = threadIdx.x; e < TC_BM * TC_BN; e += 256) {
+        const int m = m0 + e / TC_BN, n = n0 + e % TC_BN;
+        const int *a = reinterpret_cast<const int *>(At + (long long)m * ld_at);
+        const int *b = reinterpret_cast<const int *>(At + (long long)n * ld_at);
+        for (int sgi = 0; sgi < n_segs; ++sgi) {
+            const TcSeg sg = segs[sgi];
+            long long acc = 0;
+            const long long i0 = (long long)sg.kb0 * (TC_BK / 4), i1 = i0 + (long long)sg.n_kb * (TC_BK / 4);
+            int part = 0;
+            for (long long i = i0; i < i1; ++i) {
+                part = __dp4a(a[i], b[i], part);
+                if ((i & 1023) == 1023) { acc += part; part = 0; }
+            }
+            acc += part;
+            long long *o = SG + ((long long)sg.set * S + m) * S + n;
+            if (sg.first) *o = acc; else *o += acc;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ combine: digit-plane Grams -> fp64 Gram
+// G[set][c1][c2] = 2^(E1+E2) * sum_{k<=S1, l<=S2, k+l<=SMAX+1} 2^-(p_k+p_l) SG[set][plane(c1,k)][plane(c2,l)],
+// p_k = 6 + 7(k-1).  Only plane pairs with level(k) <= level(l) were computed; the others are read
+// transposed.  Terms are added from the smallest weight to the largest (fixed order).
+__global__ void __launch_bounds__(256)
+tc_combine_kernel(const long long *__restrict__ SG, long long S, const int *__restrict__ colE,
+                  const int *__restrict__ colS, const int *__restrict__ plane_row, int n_aug,
+                  double *__restrict__ G, long long ldg) {
+    const int set = blockIdx.z;
+    const int c1 = blockIdx.y;
+    const long long *SGs = SG + (long long)set * S * S;
+    double *Gs = G + (long long)set * n_aug * ldg;
+    for (int c2 = blockIdx.x * 256 + threadIdx.x; c2 < n_aug; c2 += gridDim.x * 256) {
+        if (c2 < c1) continue;                                   // upper triangle, mirrored
+        const int S1 = colS[c1], S2 = colS[c2];
+        double acc = 0.0;
+        for (int tot = TC_SMAX + 1; tot >= 2; --tot) {           // k + l = tot, smallest weights first
+            double part = 0.0;
+            for (int k = 1; k <= S1; ++k) {
+                const int l = tot - k;
+                if (l < 1 || l > S2) continue;
+                const int r1 = plane_row[c1 * TC_SMAX + (k - 1)], r2 = plane_row[c2 * TC_SMAX + (l - 1)];
+                const long long v = (k <= l) ? SGs[(long long)r1 * S + r2] : SGs[(long long)r2 * S + r1];
+                part += (double)v;                               // exact: |v| < 2^53, few terms
+            }
+            acc += scalbn(part, -(12 + 7 * (tot - 2)));
+        }
+        const double g = scalbn(acc, colE[c1] + colE[c2]);
+        Gs[(long long)c1 * ldg + c2] = g;
+        Gs[(long long)c2 * ldg + c1] = g;
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+}  // namespace sglm
+
+using namespace sglm;
+
+// Plan layout exchanged with the caller (all int32, host memory):
+//   colS_host[n_aug]            in : digit planes per column (from sglm_gram_tc_analyze_f64)
+//   set_rows_host[n_sets]       in : rows of each set
+// Derived inside (deterministic, so sizes can be queried first):
+//   plane p of column c -> row of At:  planes are laid out level-major (all columns that have a
+//   level-1 plane, then level 2, ...), each level padded to a multiple of 256 rows.
+struct TcPlan {
+    int n_aug, n_sets;
+    long long S;                        // rows of At (digit planes incl. padding), multiple of 256
+    long long n_pos;                    // columns of At (positions), multiple of 128
+    std::vector<int> plane_row;         // [n_aug * TC_SMAX]
+    std::vector<int> level_off, level_cnt;
+    std::vector<int2> tiles;
+    std::vector<TcSeg> segs;
+    std::vector<long long> set_pos0;    // first position of each set
+};
+
+static void tc_make_plan(int n_aug, const int *colS, int n_sets, const long long *set_rows, TcPlan &p) {
+    p.n_aug = n_aug; p.n_sets = n_sets;
+    p.plane_row.assign((size_t)n_aug * TC_SMAX, -1);
+    p.level_off.assign(TC_SMAX + 1, 0); p.level_cnt.assign(TC_SMAX + 1, 0);
+    long long off = 0;
+    for (int k = 1; k <= TC_SMAX; ++k) {
+        p.level_off[k] = (int)off;
+        int cnt = 0;
+        for (int c = 0; c < n_aug; ++c)
+            if (colS[c] >= k) p.plane_row[(size_t)c * TC_SMAX + (k - 1)] = (int)off + cnt++;
+        p.level_cnt[k] = cnt;
+        off += ((long long)cnt + 255) / 256 * 256;
+    }
+    p.S = std::max<long long>(off, 256);
+    // output tiles: level pairs (k <= l, k + l <= SMAX + 1)
+    p.tiles.clear();
+    for (int k = 1; k <= TC_SMAX; ++k)
+        for (int l = k; l <= TC_SMAX && k + l <= TC_SMAX + 1; ++l) {
+            if (!p.level_cnt[k] || !p.level_cnt[l]) continue;
+            const int mt0 = p.level_off[k] / TC_BM, mt1 = (p.level_off[k] + p.level_cnt[k] + TC_BM - 1) / TC_BM;
+            const int nt0 = p.level_off[l] / TC_BN, nt1 = (p.level_off[l] + p.level_cnt[l] + TC_BN - 1) / TC_BN;
+            for (int mt = mt0; mt < mt1; ++mt)
+                for (int nt = nt0; nt < nt1; ++nt) {
+                    if (k == l && (long long)(nt + 1) * TC_BN <= (long long)mt * TC_BM) continue;  // strictly below the diagonal
+                    p.tiles.push_back(make_int2(mt, nt));
+                }
+        }
+    // K segments: each set's rows padded to 128, cut into pieces that cannot overflow int32
+    p.segs.clear(); p.set_pos0.assign(n_sets, 0);
+    long long pos = 0;
+    for (int s = 0; s < n_sets; ++s) {
+        p.set_pos0[s] = pos;
+        long long kb = (set_rows[s] + TC_BK - 1) / TC_BK;
+        long long kb0 = pos / TC_BK;
+        int first = 1;
+        if (kb == 0) { p.segs.push_back(TcSeg{(int)kb0, 0, s, 1}); }
+        while (kb > 0) {
+            const int n = (int)std::min<long long>(kb, TC_MAX_KB_PER_SEG);
+            p.segs.push_back(TcSeg{(int)kb0, n, s, first});
+            first = 0; kb0 += n; kb -= n;
+        }
+        pos += (set_rows[s] + TC_BK - 1) / TC_BK * TC_BK;
+    }
+    p.n_pos = std::max<long long>(pos, TC_BK);
+}
+
+static inline size_t tc_align(size_t x) { return (x + 1023) & ~(size_t)1023; }
+
+struct TcLayout { size_t off_at, off_sg, off_plane, off_tiles, off_segs, total; };
+
+static TcLayout tc_layout(const TcPlan &p) {
+    TcLayout L;
+    size_t o = 0;
+    L.off_at = o; o += tc_align((size_t)p.S * p.n_pos);
+    L.off_sg = o; o += tc_align((size_t)p.n_sets * p.S * p.S * sizeof(long long));
+    L.off_plane = o; o += tc_align(p.plane_row.size() * sizeof(int));
+    L.off_tiles = o; o += tc_align(p.tiles.size() * sizeof(int2));
+    L.off_segs = o; o += tc_align(p.segs.size() * sizeof(TcSeg));
+    L.total = o;
+    return L;
+}
+
+// Pass 1: per-column exponent and number of digit planes (device arrays colE, colS of n_aug int32;
+// colmax_scratch: n_aug uint64; flag: 1 int32, set when the data contain NaN/inf).
+extern "C" int sglm_gram_tc_analyze_f64(const double *X, int64_t ldx, const double *Y, int64_t ldy, int32_t n_y,
+                                        int64_t T, int32_t C, int32_t *colE, int32_t *colS,
+                                        uint64_t *colmax_scratch, int32_t *flag, void *stream) {
+    SGLM_CHECK_ARG(T >= 0 && C >= 0 && n_y >= 0 && ldx >= C && ldy >= n_y, SGLM_E_SHAPE, "gram_tc_analyze: bad shape");
+    SGLM_CHECK_ARG(colE && colS && colmax_scratch && flag, SGLM_E_INVALID_ARG, "gram_tc_analyze: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_aug = C + n_y + 1;
+    SGLM_CUDA_OK(cudaMemsetAsync(colmax_scratch, 0, (size_t)n_aug * sizeof(uint64_t), st));
+    SGLM_CUDA_OK(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    const int gy = (int)std::max<long long>(1, std::min<long long>(T / 256, 64LL * sm_count() / std::max(1, ceil_div(n_aug, 256))));
+    dim3 grid(ceil_div(n_aug, 256), gy);
+    if (T > 0) {
+        tc_colmax_kernel<<<grid, 256, 0, st>>>(X, ldx, Y, ldy, C, n_y, T, (unsigned long long *)colmax_scratch);
+        SGLM_LAUNCH_OK("tc_colmax_kernel");
+    }
+    tc_exponent_kernel<<<ceil_div(n_aug, 256), 256, 0, st>>>((const unsigned long long *)colmax_scratch, n_aug, colE, colS, flag);
+    SGLM_LAUNCH_OK("tc_exponent_kernel");
+    if (T > 0) {
+        tc_digits_kernel<<<grid, 256, 0, st>>>(X, ldx, Y, ldy, C, n_y, T, colE, colS);
+        SGLM_LAUNCH_OK("tc_digits_kernel");
+    }
+    return SGLM_OK;
+}
+
+extern "C" size_t sglm_gram_tc_workspace_bytes(int32_t n_aug, const int32_t *colS_host, int32_t n_sets,
+                                               const int64_t *set_rows_host) {
+    if (n_aug <= 0 || n_sets <= 0 || !colS_host || !set_rows_host) return 0;
+    TcPlan p;
+    tc_make_plan(n_aug, colS_host, n_sets, (const long long *)set_rows_host, p);
+    return tc_layout(p).total;
+}
+
+// Plan summary for reporting: out4 = {digit-plane rows S, positions n_pos, output tiles, K segments}.
+extern "C" int sglm_gram_tc_plan_info(int32_t n_aug, const int32_t *colS_host, int32_t n_sets,
+                                      const int64_t *set_rows_host, int64_t *out4) {
+    SGLM_CHECK_ARG(n_aug > 0 && n_sets > 0 && colS_host && set_rows_host && out4, SGLM_E_INVALID_ARG,
+                   "gram_tc_plan_info: bad argument");
+    TcPlan p;
+    tc_make_plan(n_aug, colS_host, n_sets, (const long long *)set_rows_host, p);
+    out4[0] = p.S; out4[1] = p.n_pos; out4[2] = (int64_t)p.tiles.size(); out4[3] = (int64_t)p.segs.size();
+    return SGLM_OK;
+}
+
+// Pass 2: slices, int8 tcgen05 GEMM, combine.  rows: device int64 [sum of 128-padded set sizes]
+// (concatenated row lists of the sets, -1 = padding), built by the caller in set order.
+// use_check_gemm != 0 runs the CUDA-core integer GEMM instead of tcgen05 (cross-check, small sizes).
+extern "C" int sglm_gram_tc_f64(const double *X, int64_t ldx, const double *Y, int64_t ldy, int32_t n_y, int64_t T,
+                                int32_t C, const int32_t *colE, const int32_t *colS, const int32_t *colS_host,
+                                int32_t n_sets, const int64_t *set_rows_host, const int64_t *rows, double *G,
+                                int64_t ldg, void *workspace, size_t workspace_bytes, int32_t use_check_gemm,
+                                void *stream) {
+    const int n_aug = C + n_y + 1;
+    SGLM_CHECK_ARG(T >= 0 && C >= 0 && n_y >= 0 && n_sets >= 1 && ldx >= C && ldy >= n_y && ldg >= n_aug, SGLM_E_SHAPE,
+                   "gram_tc: bad shape");
+    SGLM_CHECK_ARG(colE && colS && colS_host && set_rows_host && rows && G && workspace, SGLM_E_INVALID_ARG,
+                   "gram_tc: null pointer");
+    SGLM_CHECK_ARG(((uintptr_t)workspace & 1023) == 0, SGLM_E_ALIGN, "gram_tc: workspace must be 1024-byte aligned");
+    TcPlan p;
+    tc_make_plan(n_aug, colS_host, n_sets, (const long long *)set_rows_host, p);
+    const TcLayout L = tc_layout(p);
+    SGLM_CHECK_ARG(workspace_bytes >= L.total, SGLM_E_WORKSPACE, "gram_tc: workspace too small (%zu < %zu)",
+                   workspace_bytes, L.total);
+    SGLM_CHECK_ARG(p.n_pos < 0x7fffffffLL && p.S < 0x7fffffffLL, SGLM_E_SHAPE, "gram_tc: problem too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = (char *)workspace;
+    int8_t *At = (int8_t *)(ws + L.off_at);
+    long long *SG = (long long *)(ws + L.off_sg);
+    int *d_plane = (int *)(ws + L.off_plane);
+    int2 *d_tiles = (int2 *)(ws + L.off_tiles);
+    TcSeg *d_segs = (TcSeg *)(ws + L.off_segs);
+    SGLM_CUDA_OK(cudaMemsetAsync(At, 0, (size_t)p.S * p.n_pos, st));
+    SGLM_CUDA_OK(cudaMemcpyAsync(d_plane, p.plane_row.data(), p.plane_row.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    SGLM_CUDA_OK(cudaMemcpyAsync(d_tiles, p.tiles.data(), p.tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+    SGLM_CUDA_OK(cudaMemcpyAsync(d_segs, p.segs.data(), p.segs.size() * sizeof(TcSeg), cudaMemcpyHostToDevice, st));
+    SGLM_CUDA_OK(cudaStreamSynchronize(st));        // the pageable host vectors above die with this frame
+
+    dim3 sgrid((unsigned)(p.n_pos / 128), (unsigned)ceil_div(n_aug, 32));
+    tc_slice_kernel<<<sgrid, 256, 0, st>>>(X, ldx, Y, ldy, C, n_y, (const long long *)rows, p.n_pos, colE, colS,
+                                           d_plane, At, p.n_pos);
+    SGLM_LAUNCH_OK("tc_slice_kernel");
+
+    const int n_tiles = (int)p.tiles.size();
+    if (use_check_gemm) {
+        tc_gram_i8_check_kernel<<<n_tiles, 256, 0, st>>>(At, p.n_pos, d_tiles, d_segs, (int)p.segs.size(), SG, p.S);
+        SGLM_LAUNCH_OK("tc_gram_i8_check_kernel");
+    } else {
+        PFN_encodeTiled enc = get_encode_fn();
+        SGLM_CHECK_ARG(enc != nullptr, SGLM_E_CUDA, "gram_tc: cuTensorMapEncodeTiled not available");
+        CUtensorMap tmap;
+        const cuuint64_t gdim[2] = {(cuuint64_t)p.n_pos, (cuuint64_t)p.S};
+        const cuuint64_t gstride[1] = {(cuuint64_t)p.n_pos};
+        const cuuint32_t box[2] = {(cuuint32_t)TC_BK, 128};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, At, gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SGLM_CHECK_ARG(r == CUDA_SUCCESS, SGLM_E_CUDA, "gram_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + 256;
+        SGLM_CUDA_OK(cudaFuncSetAttribute(tc_gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_gram_i8_kernel<<<n_tiles, TC_THREADS, smem, st>>>(tmap, d_tiles, d_segs, (int)p.segs.size(), SG, p.S);
+        SGLM_LAUNCH_OK("tc_gram_i8_kernel");
+    }
+    dim3 cgrid((unsigned)std::min(ceil_div(n_aug, 256), 32), (unsigned)n_aug, (unsigned)n_sets);
+    tc_combine_kernel<<<cgrid, 256, 0, st>>>(SG, p.S, colE, colS, d_plane, n_aug, G, ldg);
+    SGLM_LAUNCH_OK("tc_combine_kernel");
+    return SGLM_OK;
+}

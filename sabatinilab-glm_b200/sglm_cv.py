@@ -65,6 +65,34 @@ def _fold_weights(cv_idx, T):
     return tr, te, n_tr, n_te, comp
 
 
+def _use_tensor_core_gram(T, C):
+    """SGLM_GRAM=dmma|tc overrides; by default the tensor-core path is used once the Gram is
+    large enough for its fixed costs (two analysis passes, plan sync) to pay off."""
+    import os
+    mode = os.environ.get("SGLM_GRAM", "auto")
+    if mode == "dmma":
+        return False
+    if mode == "tc":
+        return True
+    return T * C * C >= (1 << 33)
+
+
+def _unique_sorted_rows(cv_idx, T):
+    """Sorted, duplicate-free test rows per fold as CUDA int64 tensors, or None when a test
+    list repeats rows (then the weighted fp64 path is used)."""
+    import torch
+    out = []
+    for (_, test) in cv_idx:
+        t = test if eng.is_torch(test) else torch.from_numpy(np.ascontiguousarray(np.asarray(test).reshape(-1), dtype=np.int64))
+        t = t.to(device="cuda", dtype=torch.int64)
+        t = torch.where(t < 0, t + T, t)
+        u = torch.unique(t, sorted=True)
+        if u.numel() != t.numel():
+            return None
+        out.append(u)
+    return out
+
+
 def _gaussian_grid(Xd, yd, cv_idx, glms, rolls, score_method):
     """Fit every (param set, fold) + every full-data refit of Gaussian-family GLMs.
     glms: list of sglm_.GLM objects (already dispatched to an estimator class)."""
@@ -88,14 +116,23 @@ def _gaussian_grid(Xd, yd, cv_idx, glms, rolls, score_method):
     # statistics: set 0 = full data, 1..F = test folds, then explicit train sets where the
     # train rows are not the complement of the test rows
     extra = [f for f in range(F) if not comp[f]]
-    w_rows = [torch.ones_like(yd)] + te_w + [tr_w[f] for f in extra]
-    rows_hint = [T] + n_te + [n_tr[f] for f in extra]
-    W = torch.stack(w_rows).contiguous() if len(w_rows) > 1 else None
-    G = eng.suffstats(Xd, Yd, W, rows_hint)
+    G = None
+    if not extra and _use_tensor_core_gram(T, C):
+        # 0/1 row sets: tcgen05 int8 digit-plane Gram (exact integer accumulation, fp64 result)
+        test_rows = _unique_sorted_rows(cv_idx, T)
+        if test_rows is not None:
+            G, _ = eng.suffstats_tc(Xd, Yd, [None] + test_rows)
+    if G is None:
+        # general row multiplicities: fp64 DMMA Gram with row weights
+        w_rows = [torch.ones_like(yd)] + te_w + [tr_w[f] for f in extra]
+        rows_hint = [T] + n_te + [n_tr[f] for f in extra]
+        W = torch.stack(w_rows).contiguous() if len(w_rows) > 1 else None
+        G = eng.suffstats(Xd, Yd, W, rows_hint)
+        del w_rows, W
     if not bool(torch.isfinite(G[0]).all().item()):
         raise ValueError("Input contains NaN, infinity or a value too large for dtype('float64').")
     train_set = {f: (1 + F + extra.index(f)) if f in extra else None for f in range(F)}
-    del tr_w, w_rows, W
+    del tr_w
 
     # centred problems, shared by every model with the same (row set, y column, intercept)
     problems = {}

@@ -165,6 +165,69 @@ def test_suffstats_vs_numpy(T, C, n_y, weighted, ld_pad):
     assert np.array_equal(got, np.transpose(got, (0, 2, 1)))          # exactly symmetric
 
 
+def _mixed_design(T, C, seed):
+    """Photometry-like columns: 0/1 indicators, small integers, dyadic fractions, general reals."""
+    rng = np.random.default_rng(seed)
+    X = np.empty((T, C))
+    for c in range(C):
+        kind = c % 5
+        if kind in (0, 1):
+            X[:, c] = (rng.random(T) < 0.03)
+        elif kind == 2:
+            X[:, c] = rng.integers(-5, 6, T)
+        elif kind == 3:
+            X[:, c] = rng.integers(0, 1024, T) / 1024.0
+        else:
+            X[:, c] = rng.standard_normal(T) * 10.0 ** rng.integers(-3, 4)
+    return X
+
+
+@pytest.mark.parametrize("T,C,check", [(1000, 40, True), (5000, 300, True), (40_000, 530, False)])
+def test_tensor_core_gram_matches_fp64(T, C, check):
+    """tcgen05 int8 digit-plane Gram == fp64 Gram (numpy / DMMA) to fp64 accuracy, for the full
+    set and two row subsets; with `check`, the tcgen05 GEMM is also compared bit-for-bit with
+    the CUDA-core integer GEMM run on the same digit planes."""
+    X = _mixed_design(T, C, T + C)
+    rng = np.random.default_rng(1)
+    y = rng.standard_normal((T, 2))
+    Xd, Yd = torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda()
+    sub1 = np.sort(rng.choice(T, T // 5, replace=False))
+    sub2 = np.arange(T // 3, T // 3 + 257)
+    sets = [None, torch.from_numpy(sub1).cuda(), torch.from_numpy(sub2).cuda()]
+    G, colS = eng.suffstats_tc(Xd, Yd, sets)
+    n_aug = C + 3
+    assert colS[0] == 1 and colS[2] == 1 and colS[4] == 8 and colS[-1] == 1      # indicators / ints need one plane
+    assert colS[3] <= 2
+    Z = np.concatenate([X, y, np.ones((T, 1))], axis=1)
+    for s, rows in enumerate([np.arange(T), sub1, sub2]):
+        want = Z[rows].T @ Z[rows]
+        got = G[s, :, :n_aug].cpu().numpy()
+        scale = np.sqrt(np.outer(np.diag(want), np.diag(want))) + 1e-300
+        assert np.max(np.abs(got - want) / scale) < 1e-13, s
+        assert np.array_equal(got, got.T)
+    # integer-valued columns are reproduced exactly
+    ints = [c for c in range(C) if c % 5 in (0, 1, 2)]
+    got0 = G[0, :, :n_aug].cpu().numpy()
+    assert np.array_equal(got0[np.ix_(ints, ints)], (Z[:, ints].T @ Z[:, ints]))
+    W = torch.zeros((3, T), dtype=torch.float64, device="cuda")
+    W[0] = 1.0
+    W[1, torch.from_numpy(sub1).cuda()] = 1.0
+    W[2, torch.from_numpy(sub2).cuda()] = 1.0
+    Gd = eng.suffstats(Xd, Yd, W, [T, len(sub1), len(sub2)])
+    d = (G - Gd).abs().max().item() / Gd.abs().max().item()
+    assert d < 1e-13
+    if check:
+        G2, _ = eng.suffstats_tc(Xd, Yd, sets, check_gemm=True)
+        assert torch.equal(G, G2)
+
+
+def test_tensor_core_gram_rejects_nan():
+    X = np.random.default_rng(0).standard_normal((300, 8))
+    X[17, 3] = np.inf
+    with pytest.raises(ValueError):
+        eng.suffstats_tc(torch.from_numpy(X).cuda(), torch.zeros((300, 1), dtype=torch.float64, device="cuda"), [None])
+
+
 def test_index_counts_matches_bincount():
     rng = np.random.default_rng(4)
     idx = rng.integers(-50, 1000, 5000)
