@@ -142,14 +142,15 @@ int sglm_center_stats_f64(const double *A_plus, const double *A_minus, int64_t l
  * :241 (sklearn/linear_model/_cd_fast.pyx:243-506; Gram form :1095-1290):
  * cyclic order, soft threshold, trigger d_w_max/w_max <= tol, stop on
  * gap <= tol*yy, gap-safe screening (sklearn 1.9), cold or warm start.
- * One CTA (1-8 warps, by C) per model, several models resident per SM; the rows of Q a
- * model is about to need are prefetched into a shared-memory ring with cp.async.
+ * One CTA per model, several models resident per SM; the sweep is blocked by 32 coordinates
+ * (register/shuffle phase, then one streamed panel update of the rows that moved) with
+ * iterates bit-identical to the sequential algorithm.
  *   prob_Q[p], prob_q[p], prob_diag[p] : device arrays of device pointers (Qc, qc,
  *   diag(Qc) from sglm_center_stats_f64); prob_yy[p] = yyc
  *   model m uses problem prob_of_model[m] with l1_reg[m] = alpha*l1_ratio*n and
  *   l2_reg[m] = alpha*(1-l1_ratio)*n  (_coordinate_descent.py:781-782).
  *   W[m*ldw + j] is in/out when warm_start != 0, else out (started from 0).
- *   info[m*6 + {0..5}] = {gap, tol*yy, n_iter, n_row_updates, n_rows_fetched, 0}.
+ *   info[m*6 + {0..5}] = {gap, tol*yy, n_iter, n_row_updates, n_blocks_visited, 0}.
  * ------------------------------------------------------------------------- */
 int sglm_enet_cd_gram_f64(const double *const *prob_Q, const double *const *prob_q,
                           const double *const *prob_diag, const double *prob_yy, int64_t ldq, int32_t C,

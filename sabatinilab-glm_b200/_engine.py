@@ -276,40 +276,45 @@ def solve_models(models, C, do_screening=True):
     status = np.zeros(M, dtype=np.int64)
     cd = [i for i, m in enumerate(models) if m.kind in ("lasso", "enet")]
     if cd:
-        # longest-running (small penalty) models first so the tail of the launch is short
-        cd.sort(key=lambda i: (models[i].alpha * max(models[i].l1_ratio, 1e-3)))
         probs, pidx = [], {}
         for i in cd:
             p = models[i].problem
             if id(p) not in pidx:
                 pidx[id(p)] = len(probs)
                 probs.append(p)
+        # longest-running (weakest penalty) models first so that the tail of the launch is short
+        cd.sort(key=lambda i: (models[i].alpha * max(models[i].l1_ratio, 1e-3)))
+        slots = list(cd)
+        slot_prob = [pidx[id(models[i].problem)] for i in cd]
+        n_slots = len(slots)
         ldq = probs[0].ldq
         Qp = _dev(np.array([p.Qc.data_ptr() for p in probs], dtype=np.uint64).view(np.int64), np.int64)
         qp = _dev(np.array([p.qc.data_ptr() for p in probs], dtype=np.uint64).view(np.int64), np.int64)
         dp = _dev(np.array([p.diag.data_ptr() for p in probs], dtype=np.uint64).view(np.int64), np.int64)
         yy = _dev([p.yyc for p in probs], np.float64)
         warm = any(models[i].coef_init is not None for i in cd)
-        l1 = [(models[i].alpha * models[i].l1_ratio * models[i].problem.n) for i in cd]
-        l2 = [(models[i].alpha * (1.0 - models[i].l1_ratio) * models[i].problem.n) for i in cd]
-        pack_f = _dev(np.array([l1, l2, [models[i].tol for i in cd]], dtype=np.float64), np.float64)
-        pack_i = _dev(np.array([[pidx[id(models[i].problem)] for i in cd],
-                                [models[i].max_iter for i in cd]], dtype=np.int32), np.int32)
-        Wcd = _zeros((len(cd), ldw))
+        mget = lambda i, f, pad: (f(models[i]) if i >= 0 else pad)
+        l1 = [mget(i, lambda m: m.alpha * m.l1_ratio * m.problem.n, 1.0) for i in slots]
+        l2 = [mget(i, lambda m: m.alpha * (1.0 - m.l1_ratio) * m.problem.n, 1.0) for i in slots]
+        tl = [mget(i, lambda m: m.tol, 1.0) for i in slots]
+        pack_f = _dev(np.array([l1, l2, tl], dtype=np.float64), np.float64)
+        pack_i = _dev(np.array([slot_prob, [mget(i, lambda m: m.max_iter, 0) for i in slots]], dtype=np.int32), np.int32)
+        Wcd = _zeros((n_slots, ldw))
         if warm:
-            init = np.zeros((len(cd), ldw))
-            for r, i in enumerate(cd):
-                if models[i].coef_init is not None:
+            init = np.zeros((n_slots, ldw))
+            for r, i in enumerate(slots):
+                if i >= 0 and models[i].coef_init is not None:
                     init[r, :C] = np.asarray(models[i].coef_init, dtype=np.float64).reshape(-1)
             Wcd.copy_(torch.from_numpy(init))
-        info_d = _empty((len(cd), 6))
+        info_d = _zeros((n_slots, 6))
         call("sglm_enet_cd_gram_f64", ptr(Qp), ptr(qp), ptr(dp), ptr(yy), ldq, C, ptr(pack_i[0]), ptr(pack_f[0]),
-             ptr(pack_f[1]), ptr(pack_f[2]), ptr(pack_i[1]), len(cd), int(warm), int(do_screening),
+             ptr(pack_f[1]), ptr(pack_f[2]), ptr(pack_i[1]), n_slots, int(warm), int(do_screening),
              ptr(Wcd), ldw, ptr(info_d), stream_ptr())
-        cd_t = _dev(cd, np.int64)
-        W.index_copy_(0, cd_t, Wcd)
-        info[cd] = info_d.cpu().numpy()
-        status[cd] = (info[cd, 0] > info[cd, 1]).astype(np.int64)      # 1 = duality gap above tolerance
+        real = [r for r, i in enumerate(slots) if i >= 0]
+        dst = [slots[r] for r in real]
+        W.index_copy_(0, _dev(dst, np.int64), Wcd.index_select(0, _dev(real, np.int64)))
+        info[dst] = info_d.cpu().numpy()[real]
+        status[dst] = (info[dst, 0] > info[dst, 1]).astype(np.int64)      # 1 = duality gap above tolerance
     groups = {}
     for i, m in enumerate(models):
         if m.kind in ("ridge", "ols"):

@@ -81,25 +81,38 @@ __device__ __forceinline__ void cta_reduce(double (&v)[K], double *scratch) {
     }
 }
 
-constexpr int CD_CH = 4;   // 16-byte chunks of Qw owned by one thread per pass of the panel update
+// Blocked coordinate descent, one CTA per model.
+//
+// Cyclic coordinate descent is sequential — coordinate j+1 needs the Qw produced by coordinate
+// j — so a one-coordinate-at-a-time kernel is bound by the latency of its own instruction chain
+// (measured ~2400 cycles per update, profiles/r1_cd_variants.txt).  The sweep is therefore
+// blocked by 32 consecutive coordinates:
+//
+//   phase 1 (warp 0, registers + shuffles): lane l owns coordinate 32b+l and its Qw entry; the
+//     diagonal 32x32 sub-block of Q sits in shared memory (fetched with cp.async while the
+//     previous panel update runs).  The block's coordinates are visited in order, each delta is
+//     broadcast with a shuffle and folded into the other lanes' Qw — the exact FMA sequence of
+//     the unblocked algorithm;
+//   phase 2 (panel warps): the rows of Q whose coefficient moved are streamed once
+//     (RG*CH independent 16-byte loads in flight per thread) and applied to all of Qw,
+//     Qw[k] = fma(delta_i, Q[i][k], Qw[k]) in coordinate order — again the same FMA sequence
+//     per element, so the iterates are bit-identical to the sequential algorithm.
+//
+// ncu on the first blocked version showed every unit idle (L2 12 %, FP64 5 %, issue 12 %) with
+// one 9-warp CTA per SM: the kernel is bound by latency x occupancy.  Hence the register diet
+// (sub-block in shared memory, small panel tiles): several CTAs per SM so that one model's
+// register phase overlaps other models' panel updates.
+// Active sets are bit masks over the coordinate blocks (gap-safe screening only clears bits);
+// the duality gap / screening / stopping rule run warp-locally in warp 0.
+// Shared memory per model: w, Qw, two 32x32 sub-block buffers (no copy of Q).
+__device__ __forceinline__ void cd_cp_async8(void *smem, const void *gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cd_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cd_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-// One CTA (NW warps) per model.  Cyclic coordinate descent is sequential — coordinate j+1
-// needs the Qw produced by coordinate j — so a one-coordinate-at-a-time kernel is bound by
-// the latency of its own instruction chain (measured: ~2400 cycles per update, ncu
-// profiles/r1_v2_cd_one_*).  The sweep is therefore blocked 32 coordinates at a time:
-//
-//   phase 1 (warp 0, registers + shuffles only): lane l owns coordinate j_l of the block,
-//     its Qw[j_l] and the column Q[j_0..j_31][j_l] of the 32x32 diagonal sub-block; the 32
-//     coordinates are visited in order, each delta is broadcast with a shuffle and folded
-//     into the other lanes' Qw[j_l] — the exact FMA sequence of the unblocked algorithm;
-//   phase 2 (all warps): the 32 deltas are applied to all of Qw at once,
-//     Qw[k] = fma(delta_i, Q[j_i][k], Qw[k]) for i in block order (again the same FMA
-//     sequence per element), streaming only the rows whose coefficient moved, many
-//     independent 16-byte loads in flight per thread — this is the HBM/L2-bound part.
-//
-// The iterates are bit-identical to the one-coordinate-at-a-time formulation; only the
-// schedule changes.  Shared memory per model: w, Qw, the active list (no copy of Q).
-template <int NB, int CD_RG, int MINB>
+template <int NB, int CH, int RG, int MINB>
 __global__ void __launch_bounds__((NB + 1) * 32, MINB)
 enet_cd_gram_kernel(const double *const *__restrict__ prob_Q, const double *const *__restrict__ prob_q,
                     const double *const *__restrict__ prob_diag, const double *__restrict__ prob_yy,
@@ -107,288 +120,294 @@ enet_cd_gram_kernel(const double *const *__restrict__ prob_Q, const double *cons
                     const double *__restrict__ l1_reg, const double *__restrict__ l2_reg,
                     const double *__restrict__ tol_in, const int *__restrict__ max_iter_in, int warm_start,
                     int do_screening, double *__restrict__ W, long long ldw, double *__restrict__ info) {
-    constexpr int NW = NB + 1;              // warp 0: sequential phase; warps 1..NB: panel update
-    constexpr int NT = NW * 32;
+    constexpr int NT = (NB + 1) * 32;
     constexpr int NTB = NB * 32;
     extern __shared__ __align__(16) double sm[];
     const int Cp = (C + 1) & ~1;
-    double *w = sm;                         // [Cp]
-    double *Qw = w + Cp;                    // [Cp]  (element C, when C is odd, is a harmless pad)
-    double *scratch = Qw + Cp;              // [NW * 8]
-    double *dlt = scratch + NW * 8;         // [32] deltas of the rows to stream (compacted)
-    int *active = reinterpret_cast<int *>(dlt + 32);                           // [C]
-    int *jb = active + C;                                                      // [32] their coordinates
-    int *iscr = jb + 32;                                                       // [NW + 2]
-    unsigned char *state = reinterpret_cast<unsigned char *>(iscr + NW + 2);   // [C] 2 = to-drop
+    const int NBLK = (C + 31) >> 5;
+    double *w = sm;                                   // [Cp]
+    double *Qw = w + Cp;                              // [Cp]  (element C, when C is odd, is a harmless pad)
+    double *blk = Qw + Cp;                            // [2][32][32] diagonal sub-block, double buffered
+    double *qd = blk + 2 * 1024;                      // [2][2][32]  q and diag of the block, double buffered
+    double *dlt = qd + 128;                           // [32] deltas of the current block
+    unsigned *act = reinterpret_cast<unsigned *>(dlt + 32);       // [NBLK] active-coordinate masks
+    unsigned *drp = act + NBLK;                       // [NBLK] screened-out coordinates with w != 0
+    unsigned *ctl = drp + NBLK;                       // [0] rows moved in the current block, [1] done
 
-    const int m = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int pid = prob_of_model[m];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int mdl = blockIdx.x;
+    const int pid = prob_of_model[mdl];
     const double *__restrict__ Q = prob_Q[pid];
     const double *__restrict__ q = prob_q[pid];
     const double *__restrict__ dg = prob_diag[pid];
     const double yy = prob_yy[pid];
-    const double l1 = l1_reg[m], l2 = l2_reg[m];
-    const double d_w_tol = tol_in[m];
+    const double l1 = l1_reg[mdl], l2 = l2_reg[mdl];
+    const double d_w_tol = tol_in[mdl];
     const double tol = d_w_tol * yy;
-    const int max_iter = max_iter_in[m];
+    const int max_iter = max_iter_in[mdl];
     const bool vec2 = ((ldq & 1) == 0) && ((reinterpret_cast<uintptr_t>(Q) & 15) == 0) && (ldq >= Cp);
     const int Cp2 = Cp >> 1;
+    const bool is_seq = warp == 0;
+    const bool screening = do_screening && (l1 != 0.0);
+
+    for (int i = tid; i < Cp; i += NT) { w[i] = (warm_start && i < C) ? W[(long long)mdl * ldw + i] : 0.0; Qw[i] = 0.0; }
+    if (tid == 0) { ctl[0] = 0u; ctl[1] = 0u; }
+    for (int b = tid; b < NBLK; b += NT) {
+        const int rem = C - (b << 5);
+        act[b] = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+        drp[b] = 0u;
+    }
+    __syncthreads();
+
+    double gap = 0.0, dual_norm = 0.0;
+    int n_iter = 0;
+    bool done = false;
     long long n_upd = 0, n_blk = 0;
 
-    // Qw += a * Q[j, :]   (single-row path: warm start, screening drops)
-    auto axpy_row = [&](int j, double a) {
+    // warp-local  Qw += a * Q[j, :]   (warm start, screening drops: rare)
+    auto axpy_row_warp = [&](int j, double a) {
         const double *row = Q + (long long)j * ldq;
-#pragma unroll 8
-        for (int k = tid; k < C; k += NT) Qw[k] += a * __ldg(row + k);
+        for (int k = lane; k < C; k += 32) Qw[k] += a * __ldg(row + k);
+        __syncwarp();
     };
-
-    for (int j = tid; j < Cp; j += NT) {
-        w[j] = (warm_start && j < C) ? W[(long long)m * ldw + j] : 0.0;
-        Qw[j] = 0.0;
-        if (j < C) state[j] = 0;
-    }
-    cta_sync<NW>();
-    if (warm_start) {
-        for (int j = 0; j < C; ++j) {
-            const double wj = w[j];
-            if (wj != 0.0) { axpy_row(j, wj); ++n_upd; }
-        }
-        cta_sync<NW>();
-    }
-
-    // duality gap (sklearn _cd_fast.pyx:1006-1092 gap_enet_gram); uniform result in all threads
-    double dual_norm = 0.0;
+    // duality gap (sklearn _cd_fast.pyx:1006-1092 gap_enet_gram), warp-local
     auto compute_gap = [&]() -> double {
-        double v[6] = {0, 0, 0, 0, 0, 0};   // ww, wq, wQw, |w|_1, sum xta^2, max |xta|
-        for (int j = tid; j < C; j += NT) {
+        double v0 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0, v5 = 0;   // ww, wq, wQw, |w|_1, sum xta^2, max |xta|
+        for (int j = lane; j < C; j += 32) {
             const double wj = w[j], Qwj = Qw[j], qj = __ldg(q + j);
-            v[0] += wj * wj;
-            v[1] += wj * qj;
-            v[2] += wj * Qwj;
-            v[3] += fabs(wj);
+            v0 += wj * wj; v1 += wj * qj; v2 += wj * Qwj; v3 += fabs(wj);
             const double xta = (l1 == 0.0) ? (qj - Qwj) : (qj - Qwj - l2 * wj);
-            v[4] += xta * xta;
-            v[5] = fmax(v[5], fabs(xta));
+            v4 += xta * xta;
+            v5 = fmax(v5, fabs(xta));
         }
-        cta_reduce<NW, 6, 5>(v, scratch);
-        const double R2 = yy + v[2] - 2.0 * v[1];
-        const double Ry = yy - v[1];
-        const double w22 = (l2 > 0.0) ? v[0] : 0.0;
+        v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3 = warp_sum(v3); v4 = warp_sum(v4);
+        v5 = warp_max(v5);
+        const double R2 = yy + v2 - 2.0 * v1;
+        const double Ry = yy - v1;
+        const double w22 = (l2 > 0.0) ? v0 : 0.0;
         if (l1 == 0.0) {
-            dual_norm = v[4];
-            if (l2 == 0.0) return v[4];
-            return R2 + 0.5 * l2 * w22 - Ry + 1.0 / (2.0 * l2) * v[4];
+            dual_norm = v4;
+            if (l2 == 0.0) return v4;
+            return R2 + 0.5 * l2 * w22 - Ry + 1.0 / (2.0 * l2) * v4;
         }
-        dual_norm = v[5];
-        const double primal = 0.5 * (R2 + l2 * w22) + l1 * v[3];
+        dual_norm = v5;
+        const double primal = 0.5 * (R2 + l2 * w22) + l1 * v3;
         const double scale = (dual_norm > l1) ? l1 / dual_norm : 1.0;
         const double dual = -0.5 * scale * scale * (R2 + l2 * w22) + scale * Ry;
         return primal - dual;
     };
-
-    const bool screening = do_screening && (l1 != 0.0);
-    int n_active = C;
-    for (int j = tid; j < C; j += NT) active[j] = j;
-
-    // gap-safe screening (sklearn _cd_fast.pyx:1187-1208, :1259-1279).  Ordered compaction
-    // of the surviving coordinates; dropped non-zero coordinates are applied afterwards in
-    // ascending order (XtA is evaluated from the pre-drop Qw, as in sklearn).
-    auto screen = [&](double gap, bool initial) {
+    // gap-safe screening (sklearn _cd_fast.pyx:1187-1208, :1259-1279), warp-local: clears mask
+    // bits; dropped non-zero coordinates are applied afterwards in ascending order (XtA is taken
+    // from the pre-drop Qw, as in sklearn).
+    auto screen = [&](bool initial) {
         const double radius = sqrt(2.0 * fabs(gap)) / l1;
         const double denom = fmax(l1, dual_norm);
-        const int n_cand = initial ? C : n_active;
-        int n_new = 0, any_drop = 0;
-        for (int base = 0; base < n_cand; base += NT) {
-            const int idx = base + tid;
-            int j = -1, keep = 0;
-            if (idx < n_cand) {
-                j = initial ? idx : active[idx];
+        bool any_drop = false;
+        for (int b = 0; b < NBLK; ++b) {
+            const int j = (b << 5) + lane;
+            const bool in = (j < C) && ((act[b] >> lane) & 1u);
+            bool keep = false, drop_nz = false;
+            if (in) {
                 const double djj = __ldg(dg + j);
                 if (initial && djj == 0.0) {
                     w[j] = 0.0;
                 } else {
                     const double xta = __ldg(q + j) - Qw[j] - l2 * w[j];
                     const double d_j = (1.0 - fabs(xta / denom)) / sqrt(djj + l2);
-                    if (d_j <= radius) keep = 1;
-                    else if (w[j] != 0.0) { state[j] = 2; any_drop = 1; }
+                    if (d_j <= radius) keep = true;
+                    else if (w[j] != 0.0) drop_nz = true;
                 }
             }
-            const unsigned bal = __ballot_sync(0xffffffffu, keep);
-            const int pre = __popc(bal & ((1u << lane) - 1));
-            int woff = 0, tot = __popc(bal);
-            if (NW > 1) {
-                if (lane == 0) iscr[warp] = tot;
-                __syncthreads();
-                tot = 0;
-                for (int ww = 0; ww < NW; ++ww) {
-                    const int c = iscr[ww];
-                    if (ww < warp) woff += c;
-                    tot += c;
-                }
-            } else {
-                __syncwarp();
-            }
-            if (keep) active[n_new + woff + pre] = j;
-            n_new += tot;
-            cta_sync<NW>();
+            const unsigned km = __ballot_sync(0xffffffffu, keep), dm = __ballot_sync(0xffffffffu, drop_nz);
+            if (lane == 0) { act[b] = km; drp[b] = dm; }
+            any_drop |= (dm != 0);
         }
-        n_active = n_new;
-        any_drop = __syncthreads_or(any_drop);
+        __syncwarp();
         if (any_drop) {
-            for (int j = 0; j < C; ++j) {
-                if (state[j] == 2) {          // uniform: state is only written before the barrier above
+            for (int b = 0; b < NBLK; ++b) {
+                unsigned dm = drp[b];
+                while (dm) {
+                    const int j = (b << 5) + __ffs(dm) - 1;
+                    dm &= dm - 1;
                     const double wj = w[j];
-                    cta_sync<NW>();
-                    axpy_row(j, -wj);
-                    if (tid == 0) { w[j] = 0.0; state[j] = 0; }
+                    __syncwarp();
+                    axpy_row_warp(j, -wj);
+                    if (lane == 0) w[j] = 0.0;
                     ++n_upd;
-                    cta_sync<NW>();
+                    __syncwarp();
                 }
             }
         }
     };
 
-    double gap = compute_gap();
-    int n_iter = 0;
-    bool done = (gap >= 0.0 && gap <= tol) || max_iter <= 0;
-    if (!done) {
-        if (screening) screen(gap, true);
-        cta_sync<NW>();
-        for (n_iter = 0; n_iter < max_iter; ++n_iter) {
-            double wmax_l = 0.0, dwmax_l = 0.0;            // per-lane maxima (warp 0)
-            const int n_blocks = (n_active + 31) >> 5;
-            // block registers of warp 0: coordinate, q, diag, 1/(diag+l2), column of the diagonal sub-block
-            int j_l = 0;
-            bool ok_l = false, valid_l = false;
-            double q_l = 0.0, d_l = 0.0, inv_l = 0.0, den_l = 1.0;
-            double col[32];
-            auto load_block = [&](int b) {
-                const int pos = (b << 5) + lane;
-                valid_l = pos < n_active;
-                j_l = valid_l ? active[pos] : 0;
-                q_l = valid_l ? __ldg(q + j_l) : 0.0;
-                d_l = valid_l ? __ldg(dg + j_l) : 0.0;
-                ok_l = valid_l && d_l != 0.0;
-                den_l = ok_l ? d_l + l2 : 1.0;
-                inv_l = 1.0 / den_l;
-                const int nb = min(32, n_active - (b << 5));
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int ji = (i < nb) ? active[(b << 5) + i] : 0;          // smem broadcast
-                    col[i] = (i < nb && valid_l) ? __ldg(Q + (long long)ji * ldq + j_l) : 0.0;
-                }
-            };
-            if (warp == 0 && n_blocks > 0) load_block(0);
-
-            for (int b = 0; b < n_blocks; ++b) {
-                if (warp == 0) {
-                    // ---------------- phase 1: the 32 coordinates of the block, in order
-                    double Qw_l = valid_l ? Qw[j_l] : 0.0;
-                    const double w_l = valid_l ? w[j_l] : 0.0;
-                    const double wd_l = w_l * d_l;
-                    double w_new_l = w_l, delta_l = 0.0;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const double tmp = (q_l - Qw_l) + wd_l;
-                        const double soft = copysign(fmax(fabs(tmp) - l1, 0.0), tmp);
-                        double cand = soft * inv_l;
-                        cand = fma(fma(-den_l, cand, soft), inv_l, cand);     // one Newton step: soft / den
-                        const double dc = ok_l ? cand - w_l : 0.0;
-                        const double di = __shfl_sync(0xffffffffu, dc, i);
-                        if (lane == i) { w_new_l = ok_l ? cand : w_l; delta_l = dc; }
-                        Qw_l = fma(di, col[i], Qw_l);
-                    }
-                    const unsigned nz = __ballot_sync(0xffffffffu, delta_l != 0.0);
-                    if (ok_l) {
-                        dwmax_l = fmax(dwmax_l, fabs(delta_l));
-                        wmax_l = fmax(wmax_l, fabs(w_new_l));
-                    }
-                    if (delta_l != 0.0) {
-                        w[j_l] = w_new_l;
-                        const int slot = __popc(nz & ((1u << lane) - 1));          // compacted, block order
-                        dlt[slot] = delta_l;
-                        jb[slot] = j_l;
-                    }
-                    if (lane == 0) iscr[NW + 1] = __popc(nz);
-                    n_upd += __popc(nz);
-                    ++n_blk;
-                    if (b + 1 < n_blocks) load_block(b + 1);      // in flight during phase 2
-                }
-                cta_sync<NW>();
-                // ---------------- phase 2: Qw += sum_i delta_i Q[j_i, :]   (rows in block order)
-                const int n_rows = iscr[NW + 1];
-                if (n_rows > 0 && warp > 0) {
-                    const int bt = tid - 32;
-                    if (vec2) {
-                        const double2 *Q2 = reinterpret_cast<const double2 *>(Q);
-                        double2 *Qw2 = reinterpret_cast<double2 *>(Qw);
-                        const long long ld2 = ldq >> 1;
-                        for (int c0 = bt; c0 < Cp2; c0 += NTB * CD_CH) {
-                            double2 acc[CD_CH];
-#pragma unroll
-                            for (int u = 0; u < CD_CH; ++u) {
-                                const int c = c0 + u * NTB;
-                                acc[u] = (c < Cp2) ? Qw2[c] : make_double2(0.0, 0.0);
-                            }
-                            for (int r0 = 0; r0 < n_rows; r0 += CD_RG) {
-                                double2 v[CD_RG][CD_CH];
-                                double dl[CD_RG];
-#pragma unroll
-                                for (int rr = 0; rr < CD_RG; ++rr) {
-                                    const bool rok = r0 + rr < n_rows;
-                                    dl[rr] = rok ? dlt[r0 + rr] : 0.0;
-                                    const double2 *row = Q2 + (long long)jb[rok ? r0 + rr : r0] * ld2;
-#pragma unroll
-                                    for (int u = 0; u < CD_CH; ++u) {
-                                        const int c = c0 + u * NTB;
-                                        v[rr][u] = (c < Cp2) ? __ldg(row + c) : make_double2(0.0, 0.0);
-                                    }
-                                }
-#pragma unroll
-                                for (int rr = 0; rr < CD_RG; ++rr)
-#pragma unroll
-                                    for (int u = 0; u < CD_CH; ++u) {
-                                        acc[u].x = fma(dl[rr], v[rr][u].x, acc[u].x);
-                                        acc[u].y = fma(dl[rr], v[rr][u].y, acc[u].y);
-                                    }
-                            }
-#pragma unroll
-                            for (int u = 0; u < CD_CH; ++u) {
-                                const int c = c0 + u * NTB;
-                                if (c < Cp2) Qw2[c] = acc[u];
-                            }
-                        }
-                    } else {
-                        for (int k = bt; k < C; k += NTB) {
-                            double a = Qw[k];
-                            for (int r = 0; r < n_rows; ++r) a = fma(dlt[r], __ldg(Q + (long long)jb[r] * ldq + k), a);
-                            Qw[k] = a;
-                        }
-                    }
-                }
-                cta_sync<NW>();
-            }
-            // sweep maxima (uniform in all threads)
-            double mx[2] = {warp == 0 ? wmax_l : 0.0, warp == 0 ? dwmax_l : 0.0};
-            cta_reduce<NW, 2, 0>(mx, scratch);
-            const double w_max = mx[0], d_w_max = mx[1];
-            if (w_max == 0.0 || d_w_max / w_max <= d_w_tol || n_iter == max_iter - 1) {
-                gap = compute_gap();
-                if (gap <= tol) { ++n_iter; done = true; break; }
-                if (screening) screen(gap, false);
-                cta_sync<NW>();
+    if (is_seq) {
+        if (warm_start) {
+            for (int j = 0; j < C; ++j) {
+                const double wj = w[j];
+                if (wj != 0.0) { axpy_row_warp(j, wj); ++n_upd; }
             }
         }
+        gap = compute_gap();
+        done = (gap >= 0.0 && gap <= tol) || max_iter <= 0;
+        if (!done && screening) screen(true);
+        if (lane == 0) ctl[1] = done ? 1u : 0u;
     }
-    cta_sync<NW>();
-    for (int j = tid; j < C; j += NT) W[(long long)m * ldw + j] = w[j];
-    if (tid == 0) {
-        info[6 * m + 0] = gap;
-        info[6 * m + 1] = tol;
-        info[6 * m + 2] = (double)n_iter;
-        info[6 * m + 3] = (double)n_upd;
-        info[6 * m + 4] = (double)n_upd + (double)n_blk * (32.0 * 32.0) / (double)C;   // rows fetched (equiv.)
-        info[6 * m + 5] = (double)n_blk;
+    __syncthreads();
+
+    // asynchronous fetch of block b's diagonal sub-block, q and diag into buffer `buf` (warp 0)
+    auto fetch_block = [&](int b, int buf) {
+        const int j_l = (b << 5) + lane;
+        double *dst = blk + buf * 1024;
+        if (j_l < C) {
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) {
+                const int ji = (b << 5) + i;
+                if (ji < C) cd_cp_async8(dst + i * 32 + lane, Q + (long long)ji * ldq + j_l);
+            }
+            cd_cp_async8(qd + buf * 64 + lane, q + j_l);
+            cd_cp_async8(qd + buf * 64 + 32 + lane, dg + j_l);
+        }
+        cd_cp_async_commit();
+    };
+
+    while (ctl[1] == 0u) {
+        double wmax_l = 0.0, dwmax_l = 0.0;
+        int buf = 0;
+        if (is_seq) {
+            int b0 = 0;
+            while (b0 < NBLK && act[b0] == 0u) ++b0;
+            if (b0 < NBLK) fetch_block(b0, 0);
+        }
+        for (int b = 0; b < NBLK; ++b) {
+            const unsigned mask = act[b];
+            if (mask == 0u) continue;                                     // uniform: block screened out
+            if (is_seq) {
+                // ---------------- phase 1: the block's coordinates, in order
+                cd_cp_async_wait_all();
+                __syncwarp();
+                const int j_l = (b << 5) + lane;
+                const bool inb = j_l < C;
+                const double *S = blk + buf * 1024;
+                const double q_l = inb ? qd[buf * 64 + lane] : 0.0;
+                const double d_l = inb ? qd[buf * 64 + 32 + lane] : 0.0;
+                const double den_l = (d_l != 0.0) ? d_l + l2 : 1.0;
+                const double inv_l = 1.0 / den_l;
+                const bool ok_l = ((mask >> lane) & 1u) && d_l != 0.0;
+                double Qw_l = inb ? Qw[j_l] : 0.0;
+                const double w_l = inb ? w[j_l] : 0.0;
+                const double wd_l = w_l * d_l;
+                double w_new_l = w_l, delta_l = 0.0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (!((mask >> i) & 1u)) continue;                    // uniform: coordinate screened out
+                    const double s_il = inb ? S[i * 32 + lane] : 0.0;
+                    const double tmp = (q_l - Qw_l) + wd_l;
+                    const double soft = copysign(fmax(fabs(tmp) - l1, 0.0), tmp);
+                    double cand = soft * inv_l;
+                    cand = fma(fma(-den_l, cand, soft), inv_l, cand);     // one Newton step: soft / den
+                    const double dc = ok_l ? cand - w_l : 0.0;
+                    const double di = __shfl_sync(0xffffffffu, dc, i);
+                    if (lane == i) { w_new_l = ok_l ? cand : w_l; delta_l = dc; }
+                    Qw_l = fma(di, s_il, Qw_l);
+                }
+                const unsigned nz = __ballot_sync(0xffffffffu, delta_l != 0.0);
+                if (ok_l) {
+                    dwmax_l = fmax(dwmax_l, fabs(delta_l));
+                    wmax_l = fmax(wmax_l, fabs(w_new_l));
+                }
+                if (delta_l != 0.0) w[j_l] = w_new_l;
+                dlt[lane] = delta_l;
+                if (lane == 0) ctl[0] = nz;
+                n_upd += __popc(nz);
+                ++n_blk;
+                int bn = b + 1;
+                while (bn < NBLK && act[bn] == 0u) ++bn;
+                if (bn < NBLK) fetch_block(bn, buf ^ 1);                  // lands during phase 2
+                buf ^= 1;
+            }
+            __syncthreads();                                              // deltas and moved-row mask published
+            // ---------------- phase 2: Qw += sum_i delta_i Q[32b+i, :]   (rows in coordinate order)
+            const unsigned um = ctl[0];
+            if (um && !is_seq) {
+                const int bt = tid - 32;
+                const long long row0 = (long long)(b << 5);
+                if (vec2) {
+                    const double2 *Q2 = reinterpret_cast<const double2 *>(Q) + row0 * (ldq >> 1);
+                    const long long ld2 = ldq >> 1;
+                    double2 *Qw2 = reinterpret_cast<double2 *>(Qw);
+                    for (int c0 = bt; c0 < Cp2; c0 += NTB * CH) {
+                        double2 acc[CH];
+                        bool okc[CH];
+#pragma unroll
+                        for (int u = 0; u < CH; ++u) {
+                            okc[u] = c0 + u * NTB < Cp2;
+                            acc[u] = okc[u] ? Qw2[c0 + u * NTB] : make_double2(0.0, 0.0);
+                        }
+                        unsigned rem = um;
+                        while (rem) {
+                            double2 v[RG][CH];
+                            double d[RG];
+#pragma unroll
+                            for (int r = 0; r < RG; ++r) {
+                                const int i = rem ? (__ffs(rem) - 1) : 0;
+                                d[r] = rem ? dlt[i] : 0.0;
+                                rem &= rem - 1;                           // (0 & -1) stays 0
+                                const double2 *row = Q2 + (long long)i * ld2 + c0;
+#pragma unroll
+                                for (int u = 0; u < CH; ++u)
+                                    v[r][u] = okc[u] ? __ldg(row + u * NTB) : make_double2(0.0, 0.0);
+                            }
+#pragma unroll
+                            for (int r = 0; r < RG; ++r)
+#pragma unroll
+                                for (int u = 0; u < CH; ++u) {
+                                    acc[u].x = fma(d[r], v[r][u].x, acc[u].x);
+                                    acc[u].y = fma(d[r], v[r][u].y, acc[u].y);
+                                }
+                        }
+#pragma unroll
+                        for (int u = 0; u < CH; ++u)
+                            if (okc[u]) Qw2[c0 + u * NTB] = acc[u];
+                    }
+                } else {
+                    for (int k = bt; k < C; k += NTB) {
+                        double a = Qw[k];
+                        unsigned rem = um;
+                        while (rem) {
+                            const int i = __ffs(rem) - 1;
+                            rem &= rem - 1;
+                            a = fma(dlt[i], __ldg(Q + (row0 + i) * ldq + k), a);
+                        }
+                        Qw[k] = a;
+                    }
+                }
+            }
+            __syncthreads();                                              // Qw updated
+        }
+        // ---------------- end of sweep: stopping rule / gap / screening
+        if (is_seq) {
+            const double w_max = warp_max(wmax_l), d_w_max = warp_max(dwmax_l);
+            if (w_max == 0.0 || d_w_max / w_max <= d_w_tol || n_iter == max_iter - 1) {
+                gap = compute_gap();
+                if (gap <= tol) done = true;
+                else if (screening) screen(false);
+            }
+            ++n_iter;
+            if (n_iter >= max_iter) done = true;
+            if (lane == 0) ctl[1] = done ? 1u : 0u;
+        }
+        __syncthreads();
+    }
+    if (is_seq) {
+        for (int j = lane; j < C; j += 32) W[(long long)mdl * ldw + j] = w[j];
+        if (lane == 0) {
+            info[6 * mdl + 0] = gap;
+            info[6 * mdl + 1] = tol;
+            info[6 * mdl + 2] = (double)n_iter;
+            info[6 * mdl + 3] = (double)n_upd;
+            info[6 * mdl + 4] = (double)n_blk;
+            info[6 * mdl + 5] = 0.0;
+        }
     }
 }
 
@@ -642,9 +661,9 @@ extern "C" int sglm_center_stats_f64(const double *A_plus, const double *A_minus
     return SGLM_OK;
 }
 
-static size_t cd_smem_bytes(int C, int nw) {
-    const int Cp = (C + 1) & ~1;
-    return (size_t)(2 * Cp + nw * 8 + 32) * sizeof(double) + (size_t)(C + 32 + nw + 2) * sizeof(int) + (size_t)C;
+static size_t cd_smem_bytes(int C) {
+    const int Cp = (C + 1) & ~1, nblk = (C + 31) / 32;
+    return (size_t)(2 * Cp + 2 * 1024 + 128 + 32) * sizeof(double) + (size_t)(2 * nblk + 2) * sizeof(unsigned) + 64;
 }
 
 extern "C" int sglm_enet_cd_gram_f64(const double *const *prob_Q, const double *const *prob_q,
@@ -657,27 +676,38 @@ extern "C" int sglm_enet_cd_gram_f64(const double *const *prob_Q, const double *
     if (n_models == 0) return SGLM_OK;
     SGLM_CHECK_ARG(prob_Q && prob_q && prob_diag && prob_yy && prob_of_model && l1_reg && l2_reg && tol && max_iter && W && info,
                    SGLM_E_INVALID_ARG, "enet_cd: null pointer");
-    const int nb = C <= 256 ? 1 : (C <= 512 ? 2 : (C <= 1024 ? 4 : 8));   // panel-update warps (+1 sequential warp)
-    const int nw = nb + 1;
-    const size_t smem = cd_smem_bytes(C, nw);
+    const size_t smem = cd_smem_bytes(C);
     SGLM_CHECK_ARG(smem <= 227 * 1024, SGLM_E_UNSUPPORTED,
                    "enet_cd: C=%d needs %zu bytes of shared memory per model (> 227 KB)", C, smem);
     cudaStream_t st = (cudaStream_t)stream;
-#define CD_LAUNCH(N, RG, MB)                                                                               \
+#define CD_LAUNCH(NBB, CHH, RGG, MB)                                                                       \
     do {                                                                                                   \
-        SGLM_CUDA_OK(cudaFuncSetAttribute(enet_cd_gram_kernel<N, RG, MB>,                                  \
+        SGLM_CUDA_OK(cudaFuncSetAttribute(enet_cd_gram_kernel<NBB, CHH, RGG, MB>,                          \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-        enet_cd_gram_kernel<N, RG, MB><<<n_models, (N + 1) * 32, smem, st>>>(                              \
+        enet_cd_gram_kernel<NBB, CHH, RGG, MB><<<n_models, (NBB + 1) * 32, smem, st>>>(                    \
             prob_Q, prob_q, prob_diag, prob_yy, ldq, C, prob_of_model, l1_reg, l2_reg, tol, max_iter,      \
             warm_start, do_screening, W, ldw, info);                                                       \
     } while (0)
-    // (panel warps, rows per group, min CTAs/SM) tuned on B200: the variants without register
-    // spills win; for C in (1024, 2048] one 9-warp CTA per SM (profiles/r1_cd_variants.txt)
-    switch (nb) {
-        case 1: CD_LAUNCH(1, 4, 4); break;
-        case 2: CD_LAUNCH(2, 4, 4); break;
-        case 4: CD_LAUNCH(4, 4, 2); break;
-        default: CD_LAUNCH(8, 4, 1); break;
+    // (panel warps, 16-byte chunks per thread, rows per load group, min CTAs per SM): chosen so that
+    // several models are resident per SM (profiles/r1_cd_variants.txt); SGLM_CD_VARIANT is a tuning switch
+    const char *var = getenv("SGLM_CD_VARIANT");
+    const int variant = var ? atoi(var) : 0;
+    if (C <= 256) CD_LAUNCH(1, 4, 4, 8);
+    else if (C <= 512) CD_LAUNCH(2, 4, 4, 6);
+    else if (C <= 1024) CD_LAUNCH(4, 4, 4, 4);
+    else {
+        switch (variant) {
+            case 1: CD_LAUNCH(8, 4, 4, 1); break;
+            case 2: CD_LAUNCH(8, 4, 2, 2); break;
+            case 3: CD_LAUNCH(4, 8, 2, 2); break;
+            case 4: CD_LAUNCH(4, 8, 1, 4); break;
+            case 5: CD_LAUNCH(8, 4, 2, 3); break;
+            case 6: CD_LAUNCH(16, 2, 4, 1); break;
+            case 7: CD_LAUNCH(16, 2, 2, 2); break;
+            case 8: CD_LAUNCH(8, 4, 3, 2); break;
+            case 9: CD_LAUNCH(4, 8, 2, 3); break;
+            default: CD_LAUNCH(8, 4, 2, 2); break;
+        }
     }
 #undef CD_LAUNCH
     SGLM_LAUNCH_OK("enet_cd_gram_kernel");

@@ -27,7 +27,7 @@ def run(models, label):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     Wd, info, st = eng.solve_models(models, C)
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
-    upd, fetch = info[:, 3].sum(), info[:, 4].sum()
+    upd, fetch = info[:, 3].sum(), info[:, 3].sum()
     print(f"{label:28s} models={len(models):5d} time={dt*1e3:9.1f} ms  updates={upd:.3e} fetched={fetch:.3e} "
           f"alg GB/s={upd*8*C/dt/1e9:8.1f} fetched GB/s={fetch*8*C/dt/1e9:8.1f} max n_iter={info[:,2].max():.0f} "
           f"max upd={info[:,3].max():.3e}")
