@@ -104,8 +104,8 @@ int sglm_suffstats_f64(const double *X, int64_t ldx, const double *Y, int64_t ld
  *             int64, the concatenated row lists of the sets, each padded with -1 to a multiple
  *             of 128.  G as in sglm_suffstats_f64.  use_check_gemm != 0 replaces the tcgen05
  *             GEMM by a CUDA-core integer GEMM (bit-identical results; validation only).
- *   plan_info: out4_host = {digit-plane rows S, positions, output tiles of 128x256, K segments}
- *             (issued int8 MACs = tiles * 128 * 256 * positions).
+ *   plan_info: out4_host = {digit-plane rows S, positions, output tiles of 256x256, K parts}
+ *             (issued int8 MACs = tiles * 256 * 256 * positions).
  * ------------------------------------------------------------------------- */
 int sglm_gram_tc_analyze_f64(const double *X, int64_t ldx, const double *Y, int64_t ldy, int32_t n_y,
                              int64_t T, int32_t C, int32_t *colE, int32_t *colS,

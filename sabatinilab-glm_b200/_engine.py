@@ -210,7 +210,7 @@ def suffstats_tc(Xd, Yd, set_rows, check_gemm=False):
     info = np.zeros(4, dtype=np.int64)
     nat.lib().sglm_gram_tc_plan_info(n_aug, colS_h.ctypes.data_as(ctypes.c_void_p), n_sets,
                                      sizes.ctypes.data_as(ctypes.c_void_p), info.ctypes.data_as(ctypes.c_void_p))
-    nat.last_tc_plan = dict(S=int(info[0]), n_pos=int(info[1]), tiles=int(info[2]), segs=int(info[3]),
+    nat.last_tc_plan = dict(S=int(info[0]), n_pos=int(info[1]), tiles=int(info[2]), k_parts=int(info[3]),
                             planes=int(colS_h.sum()), n_aug=n_aug)
     raw = torch.empty(ws_bytes + 1024, dtype=torch.uint8, device="cuda")
     off = (-raw.data_ptr()) % 1024

@@ -32,9 +32,9 @@ namespace sglm {
 
 constexpr int TC_SMAX = 8;       // digit planes for a general fp64 column
 constexpr int TC_BK = 128;       // K bytes (= int8 elements = design rows) per pipeline stage
-constexpr int TC_BM = 128;       // UMMA M
+constexpr int TC_BM = 256;       // output tile rows: two UMMA M=128 accumulators
 constexpr int TC_BN = 256;       // UMMA N
-constexpr int TC_STAGES = 4;
+constexpr int TC_STAGES = 3;
 constexpr int TC_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 constexpr int TC_MAX_KB_PER_SEG = 2048;   // 2048 * 128 rows * 2^12 < 2^31
 constexpr uint32_t TC_STAGE_BYTES = (TC_BM + TC_BN) * TC_BK;
@@ -116,7 +116,7 @@ tc_slice_kernel(const double *__restrict__ X, long long ldx, const double *__res
                 const int *__restrict__ colE, const int *__restrict__ colS, const int *__restrict__ plane_row,
                 int8_t *__restrict__ At, long long ld_at) {
     // plane_row[c * TC_SMAX + (k-1)] = row of At holding digit plane k of column c (or -1)
-    __shared__ double tile[128][33];
+    __shared__ __align__(16) double tile[32][130];        // [column][position], transposed on the way in
     const int n_aug = C + n_y + 1;
     const long long p0 = (long long)blockIdx.x * 128;
     const int c0 = blockIdx.y * 32;
@@ -131,22 +131,29 @@ tc_slice_kernel(const double *__restrict__ X, long long ldx, const double *__res
             const long long t = rows[p];
             if (t >= 0) v = z_value(X, ldx, Y, ldy, C, n_y, t, c);
         }
-        tile[r][cc] = v;
+        tile[cc][r] = v;
     }
     __syncthreads();
-    // thread <-> (position, 16 columns); lanes run along the positions -> 32-byte coalesced digit stores
-    const int r = tid & 127, half = tid >> 7;
-    const long long p = p0 + r;
+    // thread <-> (4 consecutive positions, 4 columns): one packed 32-bit store per digit plane,
+    // a warp writes 128 contiguous bytes of a plane row
+    const int pq = tid & 31, cg = tid >> 5;
+    const long long p = p0 + 4 * pq;
     if (p >= n_pos) return;
-    for (int cc = half * 16; cc < half * 16 + 16; ++cc) {
+#pragma unroll 1
+    for (int cc = cg * 4; cc < cg * 4 + 4; ++cc) {
         const int c = c0 + cc;
         if (c >= n_aug) break;
-        const int S = colS[c];
-        double rr = scalbn(tile[r][cc], -colE[c]) * 64.0;
+        const int S = colS[c], E = colE[c];
+        const double2 v01 = *reinterpret_cast<const double2 *>(&tile[cc][4 * pq]);
+        const double2 v23 = *reinterpret_cast<const double2 *>(&tile[cc][4 * pq + 2]);
+        double r0 = scalbn(v01.x, -E) * 64.0, r1 = scalbn(v01.y, -E) * 64.0;
+        double r2 = scalbn(v23.x, -E) * 64.0, r3 = scalbn(v23.y, -E) * 64.0;
         for (int k = 1; k <= S; ++k) {
-            const double d = rint(rr);
-            rr = (rr - d) * 128.0;
-            At[(long long)plane_row[c * TC_SMAX + (k - 1)] * ld_at + p] = (int8_t)(int)d;
+            const double d0 = rint(r0), d1 = rint(r1), d2 = rint(r2), d3 = rint(r3);
+            r0 = (r0 - d0) * 128.0; r1 = (r1 - d1) * 128.0; r2 = (r2 - d2) * 128.0; r3 = (r3 - d3) * 128.0;
+            const unsigned pack = ((unsigned)(int)d0 & 0xffu) | (((unsigned)(int)d1 & 0xffu) << 8) |
+                                  (((unsigned)(int)d2 & 0xffu) << 16) | (((unsigned)(int)d3 & 0xffu) << 24);
+            *reinterpret_cast<unsigned *>(At + (long long)plane_row[c * TC_SMAX + (k - 1)] * ld_at + p) = pack;
         }
     }
 }
@@ -212,28 +219,39 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
 }
 // instruction descriptor: dense, S32 accumulate, A/B signed int8, both K-major, M=128, N=256
 __host__ __device__ constexpr uint32_t tc_idesc_i8() {
-    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
 struct TcSeg { int kb0, n_kb, set, first; };
 
 // ------------------------------------------------------------------ the int8 tcgen05 GEMM
-// One CTA per output tile (128 x 256 of the digit-plane Gram); K runs over the row segments of all
-// sets; each segment's int32 accumulator is drained from TMEM into the int64 tile of its set.
+// One CTA per work item = (256 x 256 output tile of the digit-plane Gram, K part).  K runs over
+// this part of the row segments of all sets; each segment's int32 accumulators (two UMMA M=128
+// tiles, 512 TMEM columns) are drained into the int64 tile of its set with integer atomics —
+// exact, hence independent of the order in which the K parts arrive (deterministic result).
+// The kernel is bound by the L2 -> SM feed (~6 TB/s aggregate measured), so the tile is made as
+// square as TMEM allows: 512 operand rows per 65536 outputs.
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_gram_i8_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restrict__ tiles,
-                  const TcSeg *__restrict__ segs, int n_segs, long long *__restrict__ SG, long long S) {
+tc_gram_i8_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restrict__ tiles, int n_tiles,
+                  int n_parts, const TcSeg *__restrict__ segs, int n_segs, long long *__restrict__ SG, long long S) {
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     uint8_t *base = (uint8_t *)(((uintptr_t)tc_smem + 1023) & ~(uintptr_t)1023);
-    uint8_t *sA = base;                                           // [STAGES][128][128]
+    uint8_t *sA = base;                                           // [STAGES][256][128]
     uint8_t *sB = base + TC_STAGES * TC_BM * TC_BK;               // [STAGES][256][128]
     uint64_t *bars = (uint64_t *)(base + TC_STAGES * TC_STAGE_BYTES);
     uint64_t *full = bars, *empty = bars + TC_STAGES, *tmem_full = bars + 2 * TC_STAGES, *tmem_empty = tmem_full + 1;
     uint32_t *tmem_slot = (uint32_t *)(tmem_empty + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int2 tile = tiles[blockIdx.x];
+    const int item = blockIdx.x;
+    const int2 tile = tiles[item % n_tiles];
+    const int part = item / n_tiles;
     const int m0 = tile.x * TC_BM, n0 = tile.y * TC_BN;
+    // this item's share of segment sg: K blocks [lo, hi)
+    auto seg_range = [&](const TcSeg &sg, int &lo, int &hi) {
+        lo = sg.kb0 + (int)(((long long)sg.n_kb * part) / n_parts);
+        hi = sg.kb0 + (int)(((long long)sg.n_kb * (part + 1)) / n_parts);
+    };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
@@ -242,7 +260,7 @@ tc_gram_i8_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restri
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     tc_fence_before();
@@ -255,16 +273,19 @@ tc_gram_i8_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restri
         if (lane == 0) {
             int it = 0;
             for (int sgi = 0; sgi < n_segs; ++sgi) {
-                const TcSeg sg = segs[sgi];
-                for (int kb = 0; kb < sg.n_kb; ++kb, ++it) {
+                int lo, hi;
+                seg_range(segs[sgi], lo, hi);
+                for (int kb = lo; kb < hi; ++kb, ++it) {
                     const int st = it % TC_STAGES;
                     const uint32_t ph = (it / TC_STAGES) & 1;
                     mbar_wait(empty + st, ph ^ 1);
                     mbar_expect_tx(full + st, TC_STAGE_BYTES);
-                    const int kc = (sg.kb0 + kb) * TC_BK;
-                    tma_load_2d(sA + st * TC_BM * TC_BK, &tmap, full + st, kc, m0);
-                    tma_load_2d(sB + st * TC_BN * TC_BK, &tmap, full + st, kc, n0);
-                    tma_load_2d(sB + st * TC_BN * TC_BK + 128 * TC_BK, &tmap, full + st, kc, n0 + 128);
+                    const int kc = kb * TC_BK;
+                    uint8_t *a = sA + st * TC_BM * TC_BK, *bq = sB + st * TC_BN * TC_BK;
+                    tma_load_2d(a, &tmap, full + st, kc, m0);
+                    tma_load_2d(a + 128 * TC_BK, &tmap, full + st, kc, m0 + 128);
+                    tma_load_2d(bq, &tmap, full + st, kc, n0);
+                    tma_load_2d(bq + 128 * TC_BK, &tmap, full + st, kc, n0 + 128);
                 }
             }
         }
@@ -272,71 +293,80 @@ tc_gram_i8_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restri
         // ===== MMA issuer (one elected lane)
         if (lane == 0) {
             constexpr uint32_t idesc = tc_idesc_i8();
-            int it = 0;
+            int it = 0, drained = 0;
             for (int sgi = 0; sgi < n_segs; ++sgi) {
-                const TcSeg sg = segs[sgi];
-                if (sgi > 0) { mbar_wait(tmem_empty, (sgi - 1) & 1); tc_fence_after(); }
-                for (int kb = 0; kb < sg.n_kb; ++kb, ++it) {
+                int lo, hi;
+                seg_range(segs[sgi], lo, hi);
+                if (hi <= lo) continue;
+                if (drained > 0) { mbar_wait(tmem_empty, (drained - 1) & 1); tc_fence_after(); }
+                for (int kb = lo; kb < hi; ++kb, ++it) {
                     const int st = it % TC_STAGES;
                     const uint32_t ph = (it / TC_STAGES) & 1;
                     mbar_wait(full + st, ph);
                     tc_fence_after();
-                    const uint64_t da = umma_desc_k_sw128(smem_u32(sA + st * TC_BM * TC_BK));
+                    const uint64_t da0 = umma_desc_k_sw128(smem_u32(sA + st * TC_BM * TC_BK));
+                    const uint64_t da1 = umma_desc_k_sw128(smem_u32(sA + st * TC_BM * TC_BK + 128 * TC_BK));
                     const uint64_t db = umma_desc_k_sw128(smem_u32(sB + st * TC_BN * TC_BK));
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 32; ++k)          // UMMA K = 32 int8: +32 bytes inside the swizzle atom
-                        tc_mma_i8(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                    for (int k = 0; k < TC_BK / 32; ++k) {        // UMMA K = 32 int8: +32 bytes inside the swizzle atom
+                        const uint32_t accflag = ((kb - lo) | k) ? 1u : 0u;
+                        tc_mma_i8(tmem_acc, da0 + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, accflag);
+                        tc_mma_i8(tmem_acc + 256u, da1 + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, accflag);
+                    }
                     tc_commit(empty + st);                         // frees the stage when these MMAs retire
                 }
-                tc_commit(tmem_full);                              // accumulator of this segment complete
+                tc_commit(tmem_full);                              // accumulators of this segment complete
+                ++drained;
             }
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> int64 tile of the segment's set (sole owner, no atomics)
+        // ===== epilogue: TMEM -> registers -> int64 atomics on the tile of the segment's set
         const int q = warp & 3;                                    // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;
+        int drained = 0;
         for (int sgi = 0; sgi < n_segs; ++sgi) {
             const TcSeg sg = segs[sgi];
-            mbar_wait(tmem_full, sgi & 1);
+            int lo, hi;
+            seg_range(sg, lo, hi);
+            if (hi <= lo) continue;
+            mbar_wait(tmem_full, drained & 1);
             tc_fence_after();
-            long long *out = SG + ((long long)sg.set * S + (m0 + row)) * S + n0;
 #pragma unroll 1
-            for (int ch = 0; ch < TC_BN / 32; ++ch) {
-                uint32_t v[32];
-                const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (sg.n_kb == 0) {                              // empty row set: nothing was accumulated
+            for (int half = 0; half < 2; ++half) {
+                unsigned long long *out = reinterpret_cast<unsigned long long *>(
+                    SG + ((long long)sg.set * S + (m0 + half * 128 + row)) * S + n0);
+#pragma unroll 1
+                for (int ch = 0; ch < TC_BN / 32; ++ch) {
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 256 + ch * 32);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = 0u;
-                }
-                long long *o = out + ch * 32;
-                if (sg.first) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) o[j] = (long long)(int)v[j];
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) o[j] += (long long)(int)v[j];
+                    for (int j = 0; j < 32; ++j) {
+                        const long long x = (long long)(int)v[j];
+                        if (x != 0) atomicAdd(out + ch * 32 + j, (unsigned long long)x);
+                    }
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty);
+            ++drained;
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(256));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(512));
     }
 }
 
@@ -361,8 +391,7 @@ tc_gram_i8_check_kernel(const int8_t *__restrict__ At, long long ld_at, const in
                 if ((i & 1023) == 1023) { acc += part; part = 0; }
             }
             acc += part;
-            long long *o = SG + ((long long)sg.set * S + m) * S + n;
-            if (sg.first) *o = acc; else *o += acc;
+            SG[((long long)sg.set * S + m) * S + n] += acc;       // SG zeroed by the host; one thread per element
         }
     }
 }
@@ -435,6 +464,7 @@ struct TcPlan {
     std::vector<int> plane_row;         // [n_aug * TC_SMAX]
     std::vector<int> level_off, level_cnt;
     std::vector<int2> tiles;
+    int n_parts;                        // K parts per tile (work items = tiles * n_parts)
     std::vector<TcSeg> segs;
     std::vector<long long> set_pos0;    // first position of each set
 };
@@ -466,6 +496,23 @@ static void tc_make_plan(int n_aug, const int *colS, int n_sets, const long long
                     p.tiles.push_back(make_int2(mt, nt));
                 }
         }
+    // K parts: fill the SMs evenly (>= 3 waves when the K extent allows it)
+    {
+        const int sms = sm_count();
+        const int nt = std::max<int>(1, (int)p.tiles.size());
+        long long total_kb = 0;
+        for (int s = 0; s < n_sets; ++s) total_kb += (set_rows[s] + TC_BK - 1) / TC_BK;
+        int best = 1;
+        double best_eff = 0.0;
+        for (int parts = 1; parts <= 16; ++parts) {
+            if (parts > 1 && total_kb / parts < 64) break;
+            const long long items = (long long)nt * parts;
+            const double eff = (double)items / (double)(((items + sms - 1) / sms) * sms);
+            const double score = eff - (items < 2LL * sms ? 0.5 : 0.0) - 0.002 * parts;
+            if (score > best_eff) { best_eff = score; best = parts; }
+        }
+        p.n_parts = best;
+    }
     // K segments: each set's rows padded to 128, cut into pieces that cannot overflow int32
     p.segs.clear(); p.set_pos0.assign(n_sets, 0);
     long long pos = 0;
@@ -542,7 +589,7 @@ extern "C" int sglm_gram_tc_plan_info(int32_t n_aug, const int32_t *colS_host, i
                    "gram_tc_plan_info: bad argument");
     TcPlan p;
     tc_make_plan(n_aug, colS_host, n_sets, (const long long *)set_rows_host, p);
-    out4[0] = p.S; out4[1] = p.n_pos; out4[2] = (int64_t)p.tiles.size(); out4[3] = (int64_t)p.segs.size();
+    out4[0] = p.S; out4[1] = p.n_pos; out4[2] = (int64_t)p.tiles.size(); out4[3] = (int64_t)p.n_parts;
     return SGLM_OK;
 }
 
@@ -574,6 +621,7 @@ extern "C" int sglm_gram_tc_f64(const double *X, int64_t ldx, const double *Y, i
     int2 *d_tiles = (int2 *)(ws + L.off_tiles);
     TcSeg *d_segs = (TcSeg *)(ws + L.off_segs);
     SGLM_CUDA_OK(cudaMemsetAsync(At, 0, (size_t)p.S * p.n_pos, st));
+    SGLM_CUDA_OK(cudaMemsetAsync(SG, 0, (size_t)p.n_sets * p.S * p.S * sizeof(long long), st));
     SGLM_CUDA_OK(cudaMemcpyAsync(d_plane, p.plane_row.data(), p.plane_row.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     SGLM_CUDA_OK(cudaMemcpyAsync(d_tiles, p.tiles.data(), p.tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
     SGLM_CUDA_OK(cudaMemcpyAsync(d_segs, p.segs.data(), p.segs.size() * sizeof(TcSeg), cudaMemcpyHostToDevice, st));
@@ -602,7 +650,8 @@ extern "C" int sglm_gram_tc_f64(const double *X, int64_t ldx, const double *Y, i
         SGLM_CHECK_ARG(r == CUDA_SUCCESS, SGLM_E_CUDA, "gram_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
         const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + 256;
         SGLM_CUDA_OK(cudaFuncSetAttribute(tc_gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_gram_i8_kernel<<<n_tiles, TC_THREADS, smem, st>>>(tmap, d_tiles, d_segs, (int)p.segs.size(), SG, p.S);
+        tc_gram_i8_kernel<<<n_tiles * p.n_parts, TC_THREADS, smem, st>>>(tmap, d_tiles, n_tiles, p.n_parts, d_segs,
+                                                                        (int)p.segs.size(), SG, p.S);
         SGLM_LAUNCH_OK("tc_gram_i8_kernel");
     }
     dim3 cgrid((unsigned)std::min(ceil_div(n_aug, 256), 32), (unsigned)n_aug, (unsigned)n_sets);
