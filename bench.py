@@ -314,7 +314,10 @@ def main():
     traffic = None
     try:    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f).get(dominant, {}).get("dram_bytes_per_launch")
+            tr = json.load(f).get(dominant, {})
+            traffic = tr.get("dram_bytes_per_launch")
+            if dominant == "sglm_enet_cd_gram_f64" and tr.get("dram_bytes_per_row_update"):
+                traffic = tr["dram_bytes_per_row_update"] * n_upd       # scaled to this launch's coordinate updates
     except Exception:
         pass
     roofline = {"kernel": dominant, "bound": bound, "achieved": achieved, "peak": peak, "unit": runit,
