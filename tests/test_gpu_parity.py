@@ -484,3 +484,119 @@ def test_train_stats_identity_at_scale():
     w, b = r["cv_coefs"][:, 0], r["cv_intercepts"][0]
     assert abs(r["cv_scores_test"][0] - orc.r2_score(yh[test], Xh[test] @ w + b)) < 1e-9
     assert abs(r["cv_scores_train"][0] - orc.r2_score(yh[train], Xh[train] @ w + b)) < 1e-9
+
+
+# ------------------------------------------------------------------ BASELINE.json configurations
+def _session(T, P, h_lo, h_hi, seed, poisson=False):
+    import synth_data
+    shifts = [0] + [s for s in range(-h_lo, h_hi + 1) if s != 0]
+    X0 = synth_data.synth_base(T, P, seed)
+    Xd = orc.timeshift_multiple(X0, shift_amt_list=shifts)
+    Xd = Xd[~np.isnan(Xd).any(axis=1)]
+    y = synth_data.synth_response(Xd, synth_data.synth_kernels(P, shifts, seed), seed, poisson=poisson)
+    return X0, shifts, Xd, y
+
+
+def test_config1_single_elasticnet_fit_vs_sklearn():
+    """configs[0] shape (10 predictors x 41 shifts) at reduced T, against scikit-learn itself."""
+    from sklearn.linear_model import ElasticNet
+    X0, shifts, Xd, y = _session(20_000, 10, 20, 20, 101)
+    assert Xd.shape[1] == 410
+    design = sglm_pp.timeshift_multiple(X0, shift_amt_list=shifts)
+    assert design[20:-20].tobytes() == Xd.tobytes()
+    for alpha, l1 in [(0.01, 0.5), (0.001, 0.9)]:
+        ref = ElasticNet(alpha=alpha, l1_ratio=l1).fit(Xd, y)
+        g = sglm.GLM("Gaussian", alpha=alpha, l1_ratio=l1)
+        g.fit(Xd, y)
+        assert g.model.n_iter_ == ref.n_iter_
+        assert coef_rel_err(g.coef_, ref.coef_) < 1e-4
+        assert abs(g.intercept_ - ref.intercept_) < 1e-8
+        assert abs(g.r2_score(Xd, y) - ref.score(Xd, y)) < 1e-6
+
+
+def test_config2_ridge_cv_grid_vs_oracle():
+    """configs[1] shape (20 predictors x 61 shifts = 1220 columns, 5 folds) at reduced T."""
+    import synth_data
+    X0, shifts, Xd, y = _session(12_000, 20, 30, 30, 202)
+    assert Xd.shape[1] == 1220
+    cv_idx = synth_data.synth_folds(Xd.shape[0], 5, 202, group=500)
+    grid = [dict(alpha=float(a), l1_ratio=0, max_iter=1000, fit_intercept=True) for a in np.logspace(-3, 3, 4)]
+    want = orc.cv_glm_mult_params(Xd, y, cv_idx, "Gaussian", [dict(g) for g in grid], score_method="r2")
+    for mode in ("dmma", "tc"):
+        import os
+        os.environ["SGLM_GRAM"] = mode
+        try:
+            got = sglm_cv.cv_glm_mult_params(Xd, y, cv_idx, "Gaussian", [dict(g) for g in grid], score_method="r2")
+        finally:
+            os.environ.pop("SGLM_GRAM", None)
+        assert got["best_params"] == want["best_params"], mode
+        for a, b in zip(got["full_cv_results"], want["full_cv_results"]):
+            for k in range(5):
+                assert coef_rel_err(a["cv_coefs"][:, k], b["cv_coefs"][:, k]) < 1e-7, mode
+            assert np.allclose(a["cv_scores_test"], b["cv_scores_test"], atol=1e-6), mode
+            assert np.allclose(a["cv_scores_train"], b["cv_scores_train"], atol=1e-6), mode
+            assert abs(a["cv_R2_score"] - b["cv_R2_score"]) < 1e-6
+            assert coef_rel_err(a["model"].coef_, b["model"].coef_) < 1e-7
+
+
+def test_config4_poisson_alpha_sweep_vs_sklearn_optimum():
+    """configs[3] shape (20 predictors x 40 shifts) at reduced T, against TweedieRegressor driven
+    to its optimum (newton-cholesky, tol 1e-12)."""
+    from sklearn.linear_model import TweedieRegressor
+    X0, shifts, Xd, y = _session(15_000, 20, 20, 19, 404, poisson=True)
+    assert Xd.shape[1] == 800
+    for alpha in (1e-2, 1.0):
+        ref = TweedieRegressor(power=1, alpha=alpha, solver="newton-cholesky", tol=1e-12, max_iter=1000).fit(Xd, y)
+        g = sglm.GLM("Poisson", alpha=alpha)
+        g.fit(Xd, y)
+        assert coef_rel_err(g.coef_, ref.coef_) < 1e-6
+        assert abs(g.intercept_ - ref.intercept_) < 1e-7
+        assert abs(g.r2_score(Xd, y) - ref.score(Xd, y)) < 1e-6
+
+
+def test_full_size_properties_config2_and_3():
+    """Size-independent properties at (near) BASELINE sizes, checked with an independent fp64
+    implementation (torch): Ridge normal equations hold; ElasticNet models satisfy the duality-gap
+    stopping rule recomputed from explicit residuals; selection equals the argmax of the scores."""
+    import synth_data
+    T, P = 400_000, 20
+    shifts = [0] + [s for s in range(-30, 31) if s != 0]
+    X0 = torch.from_numpy(synth_data.synth_base(T, P, 303)).cuda()
+    X = sglm_pp.timeshift_multiple(X0, shift_amt_list=shifts)[30:T - 30]          # 399,940 x 1220 (3.9 GB)
+    n, C = X.shape
+    beta = torch.from_numpy(synth_data.synth_kernels(P, shifts, 303)).cuda()
+    y = X @ beta + 2.0 * torch.randn(n, dtype=torch.float64, device="cuda")
+    y = (y - y.mean()) / y.std()
+    cv_idx = synth_data.synth_folds(n, 3, 303, group=1000)
+    grid = [dict(alpha=1.0, l1_ratio=0, max_iter=100), dict(alpha=100.0, l1_ratio=0, max_iter=100),
+            dict(alpha=1e-3, l1_ratio=0.5, max_iter=1000), dict(alpha=1e-2, l1_ratio=0.9, max_iter=1000)]
+    res = sglm_cv.cv_glm_mult_params(X, y, cv_idx, "Gaussian", [dict(g) for g in grid], score_method="r2")
+    scores = [r["cv_R2_score"] for r in res["full_cv_results"]]
+    assert res["best_score"] == max(scores) and res["best_params"] == res["full_cv_results"][int(np.argmax(scores))]["glm_kwargs"]
+    Xc = X - X.mean(0)
+    yc = y - y.mean()
+    for r in res["full_cv_results"]:
+        kw, w = r["glm_kwargs"], torch.from_numpy(r["model"].coef_).cuda()
+        resid = yc - Xc @ w
+        if kw["l1_ratio"] == 0:                                    # (Xc'Xc + alpha I) w = Xc'yc
+            g = Xc.T @ resid - kw["alpha"] * w
+            assert g.abs().max().item() <= 1e-8 * (Xc.T @ yc).abs().max().item()
+        else:                                                      # sklearn's stopping rule: gap <= tol * ||yc||^2
+            l1 = kw["alpha"] * kw["l1_ratio"] * n
+            l2 = kw["alpha"] * (1 - kw["l1_ratio"]) * n
+            xta = Xc.T @ resid - l2 * w
+            dn = xta.abs().max().item()
+            R2, ww = float(resid @ resid), float(w @ w)
+            scale = min(1.0, l1 / dn)
+            gap = 0.5 * (R2 + l2 * ww) + l1 * float(w.abs().sum()) - (-0.5 * scale ** 2 * (R2 + l2 * ww) + scale * float(resid @ yc))
+            assert gap <= 1e-4 * float(yc @ yc) * (1 + 1e-6)
+        b = float(y.mean() - X.mean(0) @ w)
+        assert abs(b - r["model"].intercept_) < 1e-9
+    for f, (tr, te) in enumerate(cv_idx):                          # fold scores from statistics == explicit pass
+        r = res["full_cv_results"][2]
+        w = torch.from_numpy(r["cv_coefs"][:, f]).cuda()
+        te_t = torch.from_numpy(te).cuda()
+        pred = X[te_t] @ w + r["cv_intercepts"][f]
+        yt = y[te_t]
+        r2 = 1.0 - float(((yt - pred) ** 2).sum() / ((yt - yt.mean()) ** 2).sum())
+        assert abs(r2 - r["cv_scores_test"][f]) < 1e-8
