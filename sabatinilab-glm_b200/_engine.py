@@ -226,7 +226,9 @@ class Problem:
     __slots__ = ("Qc", "qc", "xbar", "diag", "scal", "ldq", "fit_intercept", "y_col", "n", "ybar", "yyc", "sy")
 
 
-def center(A_plus, A_minus, C, n_y, y_col, fit_intercept):
+def center(A_plus, A_minus, C, n_y, y_col, fit_intercept, n_rows=None):
+    """n_rows: number of rows of the set when the caller knows it (then no device read-back is
+    needed before the solvers: everything else about the problem stays on the device)."""
     ldg = A_plus.stride(0)
     ldq = _round_up(C, 8)
     p = Problem()
@@ -236,6 +238,7 @@ def center(A_plus, A_minus, C, n_y, y_col, fit_intercept):
     p.diag = _empty((C,))
     p.scal = _empty((4,))
     p.ldq, p.fit_intercept, p.y_col = ldq, bool(fit_intercept), y_col
+    p.n = float(n_rows) if n_rows is not None else None
     call("sglm_center_stats_f64", ptr(A_plus), ptr(A_minus), ldg, C, n_y, y_col, int(bool(fit_intercept)),
          ptr(p.Qc), ldq, ptr(p.qc), ptr(p.xbar), ptr(p.diag), ptr(p.scal), stream_ptr())
     return p
@@ -291,7 +294,7 @@ def solve_models(models, C, do_screening=True):
         Qp = _dev(np.array([p.Qc.data_ptr() for p in probs], dtype=np.uint64).view(np.int64), np.int64)
         qp = _dev(np.array([p.qc.data_ptr() for p in probs], dtype=np.uint64).view(np.int64), np.int64)
         dp = _dev(np.array([p.diag.data_ptr() for p in probs], dtype=np.uint64).view(np.int64), np.int64)
-        yy = _dev([p.yyc for p in probs], np.float64)
+        yy = torch.stack([p.scal for p in probs])[:, 0].contiguous()       # yyc, stays on the device
         warm = any(models[i].coef_init is not None for i in cd)
         mget = lambda i, f, pad: (f(models[i]) if i >= 0 else pad)
         l1 = [mget(i, lambda m: m.alpha * m.l1_ratio * m.problem.n, 1.0) for i in slots]
@@ -344,7 +347,14 @@ def finalize(W, C, n_y, models):
     b = _empty((M,))
     ycol = _dev([m.problem.y_col for m in models], np.int32)
     xb = _dev(np.array([m.problem.xbar.data_ptr() for m in models], dtype=np.uint64).view(np.int64), np.int64)
-    yb = _dev([m.problem.ybar for m in models], np.float64)
+    torch = nat.require_cuda()
+    uniq, where = [], {}
+    for m in models:
+        if id(m.problem) not in where:
+            where[id(m.problem)] = len(uniq)
+            uniq.append(m.problem)
+    ybar_p = torch.stack([p.scal for p in uniq])[:, 2].contiguous()
+    yb = ybar_p.index_select(0, _dev([where[id(m.problem)] for m in models], np.int64)).contiguous()
     call("sglm_finalize_models_f64", ptr(W), ldw, C, n_y, ptr(ycol), ptr(xb), ptr(yb), M, ptr(b), ptr(V), ldv,
          stream_ptr())
     return b, V

@@ -620,7 +620,18 @@ extern "C" int sglm_gram_tc_f64(const double *X, int64_t ldx, const double *Y, i
     int *d_plane = (int *)(ws + L.off_plane);
     int2 *d_tiles = (int2 *)(ws + L.off_tiles);
     TcSeg *d_segs = (TcSeg *)(ws + L.off_segs);
-    SGLM_CUDA_OK(cudaMemsetAsync(At, 0, (size_t)p.S * p.n_pos, st));
+    // the slicing pass writes every position of every real digit-plane row; only the padding rows
+    // between levels have to be cleared
+    {
+        long long covered = 0;
+        for (int k = 1; k <= TC_SMAX; ++k) {
+            const long long lo = (long long)p.level_off[k] + p.level_cnt[k];
+            const long long hi = (long long)p.level_off[k] + ((long long)p.level_cnt[k] + 255) / 256 * 256;
+            if (hi > lo) SGLM_CUDA_OK(cudaMemsetAsync(At + lo * p.n_pos, 0, (size_t)(hi - lo) * p.n_pos, st));
+            covered = std::max(covered, hi);
+        }
+        if (p.S > covered) SGLM_CUDA_OK(cudaMemsetAsync(At + covered * p.n_pos, 0, (size_t)(p.S - covered) * p.n_pos, st));
+    }
     SGLM_CUDA_OK(cudaMemsetAsync(SG, 0, (size_t)p.n_sets * p.S * p.S * sizeof(long long), st));
     SGLM_CUDA_OK(cudaMemcpyAsync(d_plane, p.plane_row.data(), p.plane_row.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     SGLM_CUDA_OK(cudaMemcpyAsync(d_tiles, p.tiles.data(), p.tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, st));

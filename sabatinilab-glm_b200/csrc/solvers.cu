@@ -603,9 +603,9 @@ finalize_models_kernel(const double *__restrict__ W, long long ldw, int C, int n
 }
 
 // --------------------------------------------------------------------------- quadratic forms  v' A v
-constexpr int QF_MB = 4;       // models per CTA
 constexpr int QF_THREADS = 256;
 
+template <int QF_MB>           // models per CTA: every row of A is streamed once for QF_MB quadratic forms
 __global__ void __launch_bounds__(QF_THREADS)
 quadform_kernel(const double *__restrict__ A, long long lda, int n, const double *__restrict__ V,
                 long long ldv, int n_models, double *__restrict__ out) {
@@ -617,10 +617,14 @@ quadform_kernel(const double *__restrict__ A, long long lda, int n, const double
         vs[e] = (mm < nm) ? V[(long long)(m0 + mm) * ldv + j] : 0.0;
     }
     __syncthreads();
-    double acc[QF_MB] = {0, 0, 0, 0};
+    double acc[QF_MB];
+#pragma unroll
+    for (int mm = 0; mm < QF_MB; ++mm) acc[mm] = 0.0;
     for (int i = warp; i < n; i += QF_THREADS / 32) {
         const double *row = A + (long long)i * lda;
-        double d[QF_MB] = {0, 0, 0, 0};
+        double d[QF_MB];
+#pragma unroll
+        for (int mm = 0; mm < QF_MB; ++mm) d[mm] = 0.0;
         for (int j = lane; j < n; j += 32) {
             const double aij = __ldg(row + j);
 #pragma unroll
@@ -756,11 +760,16 @@ extern "C" int sglm_quadform_f64(const double *A, int64_t lda, int32_t n, const 
     SGLM_CHECK_ARG(n > 0 && n_models >= 0 && lda >= n && ldv >= n, SGLM_E_SHAPE, "quadform: bad shape");
     if (n_models == 0) return SGLM_OK;
     SGLM_CHECK_ARG(A && V && out, SGLM_E_INVALID_ARG, "quadform: null pointer");
-    const size_t smem = (size_t)QF_MB * n * sizeof(double);
+    const int mb = ((size_t)8 * n * sizeof(double) <= 200 * 1024 && n_models >= 8) ? 8 : 4;
+    const size_t smem = (size_t)mb * n * sizeof(double);
     SGLM_CHECK_ARG(smem <= 227 * 1024, SGLM_E_UNSUPPORTED, "quadform: n=%d too large for shared memory", n);
-    SGLM_CUDA_OK(cudaFuncSetAttribute(quadform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    quadform_kernel<<<ceil_div(n_models, QF_MB), QF_THREADS, smem, (cudaStream_t)stream>>>(A, lda, n, V, ldv,
-                                                                                         n_models, out);
+    if (mb == 8) {
+        SGLM_CUDA_OK(cudaFuncSetAttribute(quadform_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        quadform_kernel<8><<<ceil_div(n_models, 8), QF_THREADS, smem, (cudaStream_t)stream>>>(A, lda, n, V, ldv, n_models, out);
+    } else {
+        SGLM_CUDA_OK(cudaFuncSetAttribute(quadform_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        quadform_kernel<4><<<ceil_div(n_models, 4), QF_THREADS, smem, (cudaStream_t)stream>>>(A, lda, n, V, ldv, n_models, out);
+    }
     SGLM_LAUNCH_OK("quadform_kernel");
     return SGLM_OK;
 }

@@ -129,8 +129,7 @@ def _gaussian_grid(Xd, yd, cv_idx, glms, rolls, score_method):
         W = torch.stack(w_rows).contiguous() if len(w_rows) > 1 else None
         G = eng.suffstats(Xd, Yd, W, rows_hint)
         del w_rows, W
-    if not bool(torch.isfinite(G[0]).all().item()):
-        raise ValueError("Input contains NaN, infinity or a value too large for dtype('float64').")
+    finite_flag = torch.isfinite(G[0]).all()            # read back together with the results
     train_set = {f: (1 + F + extra.index(f)) if f in extra else None for f in range(F)}
     del tr_w
 
@@ -141,11 +140,11 @@ def _gaussian_grid(Xd, yd, cv_idx, glms, rolls, score_method):
         key = (fold, ycol, bool(fi))
         if key not in problems:
             if fold is None:
-                p = eng.center(G[0], None, C, n_y, ycol, fi)
+                p = eng.center(G[0], None, C, n_y, ycol, fi, n_rows=T)
             elif train_set[fold] is None:
-                p = eng.center(G[0], G[1 + fold], C, n_y, ycol, fi)
+                p = eng.center(G[0], G[1 + fold], C, n_y, ycol, fi, n_rows=T - n_te[fold])
             else:
-                p = eng.center(G[train_set[fold]], None, C, n_y, ycol, fi)
+                p = eng.center(G[train_set[fold]], None, C, n_y, ycol, fi, n_rows=n_tr[fold])
             problems[key] = p
         return problems[key]
 
@@ -157,8 +156,7 @@ def _gaussian_grid(Xd, yd, cv_idx, glms, rolls, score_method):
             p = problem(f, ycol_of_roll[r] if f is not None else 0, est.fit_intercept)
             specs.append((est, p))
             owner.append((k, f))
-    eng.fetch_scalars(list(problems.values()))
-    models = [est._spec(p) for est, p in specs]
+    models = [est._spec(p) for est, p in specs]         # no device read-back: row counts are known on the host
     Wd, info, status = eng.solve_models(models, C)
     b_d, V = eng.finalize(Wd, C, n_y, models)
 
@@ -181,6 +179,8 @@ def _gaussian_grid(Xd, yd, cv_idx, glms, rolls, score_method):
         else:
             rss_train.index_copy_(0, sel_t, eng.quadform(G[train_set[f]], Vf))
 
+    if not bool(finite_flag.item()):
+        raise ValueError("Input contains NaN, infinity or a value too large for dtype('float64').")
     coef = Wd[:, :C].cpu().numpy()
     icpt = b_d.cpu().numpy()
     rss_test_h = rss_test.cpu().numpy()

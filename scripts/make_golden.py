@@ -238,7 +238,42 @@ def save_cv():
         json.dump(meta, f, indent=1)
 
 
+# --------------------------------------------------------------------------- #
+# 4. second-generation lag builder (sglm/sglm/features/setup_model_fit.py:43-96)
+# --------------------------------------------------------------------------- #
+def save_by_dict():
+    """The module needs the whole `sglm` package (and lab-specific imports) to import, so the two
+    functions are compiled UNMODIFIED from the reference file's AST at run time."""
+    import ast
+    path = "/root/reference/sglm/sglm/features/setup_model_fit.py"
+    tree = ast.parse(open(path).read())
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("timeshift_vals_by_dict", "X_cols_dict_to_default")]
+    ns = {"np": np, "pd": pd}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
+    rng = np.random.default_rng(21)
+    df = pd.DataFrame({"a": rng.standard_normal(60), "b": (rng.random(60) < 0.2).astype(float),
+                       "c": np.arange(60.0), "lbl": rng.integers(0, 3, 60)})
+    cases = [dict(d={"a": (-2, 3), "b": (-1, 1)}, keep_nans=False), dict(d={"b": (-3, 0), "a": (0, 2)}, keep_nans=True),
+             dict(d={"c": (-1, 4)}, keep_nans=False)]
+    blob, meta = {"df": df.to_numpy(dtype=np.float64)}, dict(versions=VERSIONS, columns=list(df.columns), cases=[])
+    for i, c in enumerate(cases):
+        out, names = ns["timeshift_vals_by_dict"](df, dict(c["d"]), keep_nans=c["keep_nans"])
+        blob[f"out{i}"] = out.to_numpy(dtype=np.float64)
+        blob[f"idx{i}"] = np.asarray(out.index)
+        meta["cases"].append(dict(d={k: list(v) for k, v in c["d"].items()}, keep_nans=c["keep_nans"],
+                                  names=names, out_columns=list(out.columns)))
+    meta["default"] = {k: list(v) for k, v in ns["X_cols_dict_to_default"]({"a": (0, 0), "b": None, "c": (-1, 2)}).items()}
+    np.savez_compressed(os.path.join(OUT, "by_dict_ref.npz"), **blob)
+    with open(os.path.join(OUT, "by_dict_ref.json"), "w") as f:
+        json.dump(meta, f, indent=1)
+    print("by_dict cases:", len(cases))
+
+
 if __name__ == "__main__":
+    if "--only-by-dict" in sys.argv:
+        save_by_dict()
+        sys.exit(0)
+    save_by_dict()
     save_gather()
     save_fits()
     save_cv()

@@ -600,3 +600,18 @@ def test_full_size_properties_config2_and_3():
         yt = y[te_t]
         r2 = 1.0 - float(((yt - pred) ** 2).sum() / ((yt - yt.mean()) ** 2).sum())
         assert abs(r2 - r["cv_scores_test"][f]) < 1e-8
+
+
+def test_second_generation_lag_builder_vs_reference_golden():
+    """`timeshift_vals_by_dict` (sglm/sglm/features/setup_model_fit.py:43-96): predictor-major layout."""
+    import setup_model_fit
+    blob, meta = load_golden("by_dict_ref")
+    df = pd.DataFrame(blob["df"], columns=meta["columns"])
+    for i, case in enumerate(meta["cases"]):
+        d = {k: tuple(v) for k, v in case["d"].items()}
+        out, names = setup_model_fit.timeshift_vals_by_dict(df, d, keep_nans=case["keep_nans"])
+        assert names == case["names"] and list(out.columns) == case["out_columns"]
+        assert np.array_equal(np.asarray(out.index), blob[f"idx{i}"])
+        assert out.to_numpy(dtype=np.float64).tobytes() == blob[f"out{i}"].tobytes()
+    got = setup_model_fit.X_cols_dict_to_default({"a": (0, 0), "b": None, "c": (-1, 2)})
+    assert {k: list(v) for k, v in got.items()} == meta["default"]
