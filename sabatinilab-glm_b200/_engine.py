@@ -332,8 +332,20 @@ def solve_models(models, C, do_screening=True):
         st = torch.empty(n_a, dtype=torch.int32, device="cuda")
         call("sglm_ridge_solve_f64", ptr(p.Qc), p.ldq, ptr(p.qc), C, ptr(alphas), n_a, ptr(Wr), ldw, ptr(st),
              ptr(work), wb, stream_ptr())
+        st_h = st.cpu().numpy()
+        for k, i in enumerate(idxs):
+            if st_h[k] != 0 and models[i].kind == "ols":
+                # rank-deficient least squares: minimum-norm solution, singular values below
+                # 1e-6 * s_max dropped — what scipy.linalg.lstsq(cond=1e-6) returns for
+                # LinearRegression (sklearn _base.py:750-753).  Rare path; dense symmetric
+                # eigensolver from the CUDA libraries, still on the device.
+                lam, Vec = torch.linalg.eigh(p.Qc[:, :C])
+                keep = lam > (1e-6 ** 2) * lam.max().clamp_min(0.0)
+                inv = torch.where(keep, 1.0 / torch.where(keep, lam, torch.ones_like(lam)), torch.zeros_like(lam))
+                Wr[k, :C] = Vec @ (inv * (Vec.T @ p.qc))
+                st_h[k] = 0
         W.index_copy_(0, _dev(idxs, np.int64), Wr)
-        status[idxs] = st.cpu().numpy() * 2                            # 2 = not positive definite
+        status[idxs] = st_h * 2                                        # 2 = not positive definite
         del work
     return W, info, status
 

@@ -615,3 +615,20 @@ def test_second_generation_lag_builder_vs_reference_golden():
         assert out.to_numpy(dtype=np.float64).tobytes() == blob[f"out{i}"].tobytes()
     got = setup_model_fit.X_cols_dict_to_default({"a": (0, 0), "b": None, "c": (-1, 2)})
     assert {k: list(v) for k, v in got.items()} == meta["default"]
+
+
+def test_ols_rank_deficient_matches_lstsq_min_norm():
+    """alpha == 0 on a rank-deficient design (an all-zero column and a duplicated column):
+    scikit-learn's LinearRegression returns the minimum-norm least-squares solution."""
+    from sklearn.linear_model import LinearRegression
+    rng = np.random.default_rng(12)
+    X = rng.standard_normal((500, 12))
+    X[:, 3] = 0.0
+    X[:, 7] = X[:, 2]
+    y = X @ rng.standard_normal(12) + 0.1 * rng.standard_normal(500)
+    ref = LinearRegression().fit(X, y)
+    g = sglm.GLM("Gaussian", alpha=0, l1_ratio=0.5, max_iter=10)
+    g.fit(X, y)
+    assert coef_rel_err(g.coef_, ref.coef_) < 1e-7
+    assert abs(g.intercept_ - ref.intercept_) < 1e-9
+    assert np.allclose(g.predict(X), ref.predict(X), atol=1e-9)
