@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--l1s", type=int, default=5)
     ap.add_argument("--max-iter", type=int, default=1000)
     ap.add_argument("--tol", type=float, default=1e-4)
+    ap.add_argument("--warm-path", action="store_true",
+                    help="opt-in non-reference mode: warm-started alpha paths (NOT the parity configuration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-T", type=int, default=40_000)
@@ -87,7 +89,8 @@ def config_dict(args, n_gpus):
     return {"workload": f"ElasticNet CV grid {args.folds} folds x {args.alphas} alphas x {args.l1s} l1_ratios "
                         f"(+1 full-data refit per set = {len(grid) * (args.folds + 1)} fits/step) on "
                         f"{args.T} timepoints x {C} lagged columns (P={args.P} base signals x {len(shifts)} shifts), "
-                        f"fp64, tol={args.tol}, max_iter={args.max_iter}, cold start, cyclic CD "
+                        f"fp64, tol={args.tol}, max_iter={args.max_iter}, "
+                        f"{'WARM-STARTED alpha paths (non-reference mode)' if args.warm_path else 'cold start'}, cyclic CD "
                         f"(BASELINE.json configs[2]); one independent session per GPU",
             "T": args.T, "C": C, "folds": args.folds, "alphas": args.alphas, "l1_ratios": args.l1s,
             "fits_per_step": len(grid) * (args.folds + 1), "sessions": n_gpus,
@@ -202,6 +205,8 @@ def main():
     import _sglm_native as nat
     import sglm_cv
     import sglm_pp
+    import _engine
+    _engine.WARM_START_PATHS = bool(args.warm_path)
 
     torch.cuda.set_device(local_rank)
     if world > 1:

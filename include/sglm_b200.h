@@ -150,7 +150,7 @@ int sglm_center_stats_f64(const double *A_plus, const double *A_minus, int64_t l
  *   model m uses problem prob_of_model[m] with l1_reg[m] = alpha*l1_ratio*n and
  *   l2_reg[m] = alpha*(1-l1_ratio)*n  (_coordinate_descent.py:781-782).
  *   W[m*ldw + j] is in/out when warm_start != 0, else out (started from 0).
- *   info[m*6 + {0..5}] = {gap, tol*yy, n_iter, n_row_updates, n_blocks_visited, 0}.
+ *   info[m*6 + {0..5}] = {gap, tol*yy, n_iter, n_row_updates, n_blocks_visited, share of time in the register phase}.
  * ------------------------------------------------------------------------- */
 int sglm_enet_cd_gram_f64(const double *const *prob_Q, const double *const *prob_q,
                           const double *const *prob_diag, const double *prob_yy, int64_t ldq, int32_t C,

@@ -162,7 +162,8 @@ enet_cd_gram_kernel(const double *const *__restrict__ prob_Q, const double *cons
     double gap = 0.0, dual_norm = 0.0;
     int n_iter = 0;
     bool done = false;
-    long long n_upd = 0, n_blk = 0;
+    long long n_upd = 0, n_blk = 0, t_p1 = 0;
+    const long long t_begin = clock64();
 
     // warp-local  Qw += a * Q[j, :]   (warm start, screening drops: rare)
     auto axpy_row_warp = [&](int j, double a) {
@@ -283,6 +284,7 @@ enet_cd_gram_kernel(const double *const *__restrict__ prob_Q, const double *cons
             if (mask == 0u) continue;                                     // uniform: block screened out
             if (is_seq) {
                 // ---------------- phase 1: the block's coordinates, in order
+                const long long t_b = clock64();
                 cd_cp_async_wait_all();
                 __syncwarp();
                 const int j_l = (b << 5) + lane;
@@ -290,26 +292,30 @@ enet_cd_gram_kernel(const double *const *__restrict__ prob_Q, const double *cons
                 const double *S = blk + buf * 1024;
                 const double q_l = inb ? qd[buf * 64 + lane] : 0.0;
                 const double d_l = inb ? qd[buf * 64 + 32 + lane] : 0.0;
-                const double den_l = (d_l != 0.0) ? d_l + l2 : 1.0;
-                const double inv_l = 1.0 / den_l;
+                const double inv_l = (d_l != 0.0) ? 1.0 / (d_l + l2) : 1.0;
                 const bool ok_l = ((mask >> lane) & 1u) && d_l != 0.0;
                 double Qw_l = inb ? Qw[j_l] : 0.0;
                 const double w_l = inb ? w[j_l] : 0.0;
-                const double wd_l = w_l * d_l;
-                double w_new_l = w_l, delta_l = 0.0;
+                // Soft-threshold update written for a short dependent chain (the 32 steps are
+                // serialised through Qw_l):  with r = (q + w d) - Qw,
+                //   delta = r >  l1 ? (r - l1)/den - w : r < -l1 ? (r + l1)/den - w : -w
+                // evaluated as one FMA per branch from per-lane constants; w_new = w + delta.
+                const double a_l = fma(w_l, d_l, q_l);
+                const double k_pos = fma(-l1, inv_l, -w_l), k_neg = fma(l1, inv_l, -w_l);
+                double delta_l = 0.0;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     if (!((mask >> i) & 1u)) continue;                    // uniform: coordinate screened out
                     const double s_il = inb ? S[i * 32 + lane] : 0.0;
-                    const double tmp = (q_l - Qw_l) + wd_l;
-                    const double soft = copysign(fmax(fabs(tmp) - l1, 0.0), tmp);
-                    double cand = soft * inv_l;
-                    cand = fma(fma(-den_l, cand, soft), inv_l, cand);     // one Newton step: soft / den
-                    const double dc = ok_l ? cand - w_l : 0.0;
+                    const double r = a_l - Qw_l;
+                    const double dpos = fma(r, inv_l, k_pos), dneg = fma(r, inv_l, k_neg);
+                    double dc = (r > l1) ? dpos : ((r < -l1) ? dneg : -w_l);
+                    dc = ok_l ? dc : 0.0;
                     const double di = __shfl_sync(0xffffffffu, dc, i);
-                    if (lane == i) { w_new_l = ok_l ? cand : w_l; delta_l = dc; }
+                    if (lane == i) delta_l = dc;
                     Qw_l = fma(di, s_il, Qw_l);
                 }
+                const double w_new_l = w_l + delta_l;
                 const unsigned nz = __ballot_sync(0xffffffffu, delta_l != 0.0);
                 if (ok_l) {
                     dwmax_l = fmax(dwmax_l, fabs(delta_l));
@@ -324,6 +330,7 @@ enet_cd_gram_kernel(const double *const *__restrict__ prob_Q, const double *cons
                 while (bn < NBLK && act[bn] == 0u) ++bn;
                 if (bn < NBLK) fetch_block(bn, buf ^ 1);                  // lands during phase 2
                 buf ^= 1;
+                t_p1 += clock64() - t_b;
             }
             __syncthreads();                                              // deltas and moved-row mask published
             // ---------------- phase 2: Qw += sum_i delta_i Q[32b+i, :]   (rows in coordinate order)
@@ -406,7 +413,7 @@ enet_cd_gram_kernel(const double *const *__restrict__ prob_Q, const double *cons
             info[6 * mdl + 2] = (double)n_iter;
             info[6 * mdl + 3] = (double)n_upd;
             info[6 * mdl + 4] = (double)n_blk;
-            info[6 * mdl + 5] = 0.0;
+            info[6 * mdl + 5] = (double)t_p1 / (double)max(1LL, clock64() - t_begin);   // share of time in the register phase
         }
     }
 }

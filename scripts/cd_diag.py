@@ -30,7 +30,7 @@ def run(models, label):
     upd, fetch = info[:, 3].sum(), info[:, 3].sum()
     print(f"{label:28s} models={len(models):5d} time={dt*1e3:9.1f} ms  updates={upd:.3e} fetched={fetch:.3e} "
           f"alg GB/s={upd*8*C/dt/1e9:8.1f} fetched GB/s={fetch*8*C/dt/1e9:8.1f} max n_iter={info[:,2].max():.0f} "
-          f"max upd={info[:,3].max():.3e}")
+          f"max upd={info[:,3].max():.3e} p1share(heaviest)={info[np.argmax(info[:,3]),5]:.3f} blocks(heaviest)={info[np.argmax(info[:,3]),4]:.0f}")
     return info
 ms = specs()
 run(ms, "warm-up all")

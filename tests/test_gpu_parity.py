@@ -632,3 +632,30 @@ def test_ols_rank_deficient_matches_lstsq_min_norm():
     assert coef_rel_err(g.coef_, ref.coef_) < 1e-7
     assert abs(g.intercept_ - ref.intercept_) < 1e-9
     assert np.allclose(g.predict(X), ref.predict(X), atol=1e-9)
+
+
+def test_warm_started_paths_reach_the_same_optimum():
+    """Opt-in warm-started alpha paths: same optimum as the cold-start (reference) mode —
+    <= 1e-8 on coefficients at tol = 1e-10, and within solver tolerance at 1e-4."""
+    import synth_data
+    X0, shifts, Xd, y = _session(6000, 6, 4, 4, 55)
+    cv_idx = synth_data.synth_folds(Xd.shape[0], 3, 55, group=200)
+    def run(tol, warm):
+        grid = [dict(alpha=float(a), l1_ratio=l, max_iter=5000, tol=tol) for l in (0.2, 0.8) for a in np.logspace(-3, -1, 6)]
+        eng.WARM_START_PATHS = warm
+        try:
+            return sglm_cv.cv_glm_mult_params(Xd, y, cv_idx, "Gaussian", grid, score_method="r2")
+        finally:
+            eng.WARM_START_PATHS = False
+    cold, warm = run(1e-10, False), run(1e-10, True)
+    assert cold["best_params"] == warm["best_params"]
+    sweeps = lambda res: sum(r["_fit_info"]["cd_info"][:, 2].sum() for r in res["full_cv_results"])
+    for a, b in zip(cold["full_cv_results"], warm["full_cv_results"]):
+        assert a["glm_kwargs"] == b["glm_kwargs"]
+        for k in range(3):
+            assert coef_rel_err(b["cv_coefs"][:, k], a["cv_coefs"][:, k]) < 1e-8
+        assert np.allclose(a["cv_scores_test"], b["cv_scores_test"], atol=1e-9)
+    assert sweeps(warm) < sweeps(cold)
+    cold4, warm4 = run(1e-4, False), run(1e-4, True)
+    for a, b in zip(cold4["full_cv_results"], warm4["full_cv_results"]):
+        assert np.allclose(a["cv_scores_test"], b["cv_scores_test"], atol=1e-3)
