@@ -64,6 +64,8 @@ def device_matrix(X):
     if a.ndim != 2:
         raise ValueError(f"Expected 2D array, got {a.ndim}D array instead")
     a = np.ascontiguousarray(a, dtype=np.float64)
+    if not a.flags.writeable:
+        a = a.copy()
     return torch.from_numpy(a).to("cuda")
 
 

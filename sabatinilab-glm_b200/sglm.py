@@ -44,6 +44,11 @@ class GLM():
             kwargs['warm_start'] = True
 
         self.model_name = model_name
+        # second-generation attributes (sglm/sglm/models/sglm.py:69-71): `closed_form` is switched
+        # on by the caller after construction and turns `fit` into an un-penalised least-squares fit
+        self.closed_form = False
+        if 'fit_intercept' in kwargs:
+            self.fit_intercept = kwargs['fit_intercept']
         if model_name in {'Normal', 'Gaussian'}:
             # estimator choice by (alpha, l1_ratio) — backend/sglm.py:96-110
             if 'alpha' in kwargs and kwargs['alpha'] == 0:
@@ -114,6 +119,16 @@ class GLM():
         self.intercept_ = self.beta0_
 
     def fit(self, X, y, *args):
+        if self.closed_form:
+            # sglm/sglm/models/sglm.py:263-293: lstsq on [X | 1]; same least-squares solution as the
+            # centred OLS solve of the GPU path (minimum-norm fallback when rank-deficient)
+            ols = LinearRegression(fit_intercept=getattr(self, 'fit_intercept', True))
+            ols.fit(X, y)
+            self.coef_ = self.beta_ = ols.coef_
+            self.intercept_ = self.beta0_ = ols.intercept_
+            self.full_betas_ = np.concatenate([ols.coef_, [ols.intercept_]]) if ols.fit_intercept else ols.coef_
+            self.model.coef_, self.model.intercept_ = self.coef_, self.intercept_
+            return
         self.model.fit(X, y, *args)
         # attribute mapping of backend/sglm.py:246-251 (Poisson mapped too, see module docstring)
         self.coef_ = self.model.coef_
@@ -161,6 +176,13 @@ class GLM():
             std = np.std(resid)
             return float(np.sum(-0.5 * np.log(2 * np.pi * std * std) - resid ** 2 / (2 * std * std)))
         raise NotYetImplementedError("name 'NotYetImplementedError' is not defined")
+
+
+def fit_GLM(X, y, model_name='Gaussian', *args, **kwargs):
+    """Second-generation convenience (sglm/sglm/models/sglm.py:345-364): build, fit, return."""
+    glm = GLM(model_name, *args, **kwargs)
+    glm.fit(X, y)
+    return glm
 
 
 def calc_R2(residuals, mean_residuals):

@@ -659,3 +659,50 @@ def test_warm_started_paths_reach_the_same_optimum():
     cold4, warm4 = run(1e-4, False), run(1e-4, True)
     for a, b in zip(cold4["full_cv_results"], warm4["full_cv_results"]):
         assert np.allclose(a["cv_scores_test"], b["cv_scores_test"], atol=1e-3)
+
+
+def test_second_generation_closed_form_fit():
+    """`glm.closed_form = True` (sglm/sglm/models/sglm.py:263-293): lstsq on [X | 1]."""
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((400, 9))
+    y = X @ rng.standard_normal(9) + 2.5 + 0.1 * rng.standard_normal(400)
+    want = np.linalg.lstsq(np.concatenate([X, np.ones((400, 1))], axis=1), y, rcond=-1)[0]
+    g = sglm.GLM("Gaussian", alpha=0.1, l1_ratio=0.5, fit_intercept=True)
+    g.closed_form = True
+    g.fit(X, y)
+    assert coef_rel_err(np.append(g.coef_, g.intercept_), want) < 1e-9
+    assert np.allclose(g.predict(X), np.concatenate([X, np.ones((400, 1))], axis=1) @ want, atol=1e-9)
+    g2 = sglm.fit_GLM(pd.DataFrame(X), pd.Series(y), alpha=0.01)
+    assert g2.coef_.shape == (9,)
+
+
+def test_fit_set_in_place_semantics_from_threads():
+    """GLM.fit_set (backend/sglm.py:254-312) writes into caller-owned arrays and lists; the
+    reference calls it from 4 Python threads (backend/sglm_cv.py:162-170)."""
+    import threading
+    rng = np.random.default_rng(8)
+    X = rng.standard_normal((900, 14))
+    y = X[:, :3].sum(1) + rng.standard_normal(900)
+    folds = [(np.r_[0:600], np.r_[600:900]), (np.r_[300:900], np.r_[0:300]), (np.r_[0:300, 600:900], np.r_[300:600]),
+             (np.r_[100:800], np.r_[0:100, 800:900])]
+    n = len(folds)
+    cv_coefs, cv_icpt = np.zeros((14, n)), np.zeros(n)
+    tr, te = np.zeros(n), np.zeros(n)
+    resids, mean_resids = [], []
+    def work(k):
+        a, b = folds[k]
+        g = sglm.GLM("Gaussian", alpha=0.02, l1_ratio=0.5, score_method="r2")
+        g.fit_set(X[a], y[a], X[b], y[b], cv_coefs, cv_icpt, tr, te, k, resids=resids, mean_resids=mean_resids, id_fit=k)
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(n)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert len(resids) == n and len(mean_resids) == n
+    for k, (a, b) in enumerate(folds):
+        ref = orc.GLM("Gaussian", alpha=0.02, l1_ratio=0.5, score_method="r2").fit(X[a], y[a])
+        assert coef_rel_err(cv_coefs[:, k], ref.coef_) < 1e-4
+        assert abs(cv_icpt[k] - ref.intercept_) < 1e-8
+        assert abs(tr[k] - ref.r2_score(X[a], y[a])) < 1e-6 and abs(te[k] - ref.r2_score(X[b], y[b])) < 1e-6
+    pooled = sglm.calc_R2(np.concatenate(resids), np.concatenate(mean_resids))
+    assert -1.0 < pooled < 1.0
