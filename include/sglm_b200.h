@@ -159,6 +159,30 @@ int sglm_enet_cd_gram_f64(const double *const *prob_Q, const double *const *prob
                           int32_t n_models, int32_t warm_start, int32_t do_screening,
                           double *W, int64_t ldw, double *info, void *stream);
 
+/* Same fits, same iterates (a6), second-generation layout: one thread-block CLUSTER of
+ * cluster_size CTAs per GROUP of group_size models that share a problem (fold).  The
+ * coordinate blocks (w, Qw slice, register phase) are split over the cluster's CTAs, block
+ * deltas travel as records through distributed shared memory, the panel update of a record
+ * overlaps the next block's register phase (look-ahead), and a moved row of Q is loaded once
+ * for all models of the group.
+ *   group g uses problem prob_of_group[g]; its models are model_of_slot[g*group_size + s]
+ *   (index into l1_reg / l2_reg / tol / max_iter, row of W and info; -1 = empty slot).
+ *   Q pointers must be 16-byte aligned and ldq even.  Other arguments as above.
+ *   prob_tmap: device array (64-byte aligned) of one TMA descriptor per problem, encoded on the host by
+ *   sglm_enet_cd_cluster_encode_tmaps (Q_dev_ptrs = the same device pointers as prob_Q, as host values)
+ *   into n_prob * sglm_enet_cd_cluster_tmap_bytes() bytes and copied to the device by the caller.
+ * sglm_enet_cd_cluster_supported(group_size, cluster_size) -> 1 if that shape is compiled in. */
+int sglm_enet_cd_cluster_supported(int32_t group_size, int32_t cluster_size);
+size_t sglm_enet_cd_cluster_tmap_bytes(void);
+int sglm_enet_cd_cluster_encode_tmaps(const uint64_t *Q_dev_ptrs, int32_t n_prob, int32_t C, int64_t ldq, void *out);
+int sglm_enet_cd_cluster_f64(const double *const *prob_Q, const double *const *prob_q,
+                             const double *const *prob_diag, const double *prob_yy, int64_t ldq, int32_t C,
+                             const int32_t *prob_of_group, const int32_t *model_of_slot,
+                             const double *l1_reg, const double *l2_reg, const double *tol,
+                             const int32_t *max_iter, int32_t n_groups, int32_t group_size,
+                             int32_t cluster_size, int32_t warm_start, int32_t do_screening,
+                             double *W, int64_t ldw, double *info, const void *prob_tmap, void *stream);
+
 /* ------------------------------------------------------------------------- *
  * (a7, a8) batched Cholesky solve — Ridge / OLS.  Replaces sklearn
  * _ridge._solve_cholesky (sklearn/linear_model/_ridge.py:215-227) and the

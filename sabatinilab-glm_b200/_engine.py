@@ -277,6 +277,64 @@ def _warm_paths():
     return WARM_START_PATHS or os.environ.get("SGLM_WARM_PATH", "0") == "1"
 
 
+CD_DEBUG_TIMER = 0      # diagnostics: which timer of the cluster kernel lands in info[:, 5] (0 register phase, 1 waits, 2 publish, 3 look-ahead)
+CD_GROUP, CD_CLUSTER = None, None     # override of (models per cluster, CTAs per cluster); 0 = first-generation kernel
+
+
+CD_PLAN = None      # override of the launch plan, e.g. "4x2@0.2,4x1" (see _cd_plan)
+_SIDE_STREAMS = {}
+
+
+def _side_stream(i):
+    torch = nat.require_cuda()
+    key = (torch.cuda.current_device(), i)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream()
+    return _SIDE_STREAMS[key]
+
+
+def _cd_shape_ok(g, k, C):
+    if g <= 0 or k <= 0:
+        return 0, 0
+    while k > 1 and (C + 31) // 32 < 2 * k:
+        k //= 2
+    if not nat.lib().sglm_enet_cd_cluster_supported(g, k):
+        raise nat.SglmNativeError(f"coordinate descent: unsupported (group, cluster) = ({g}, {k})")
+    return g, k
+
+
+def _cd_plan(C, n_models):
+    """Parts of the coordinate-descent launch: [(first slot, end slot, group size M, cluster size K)] over
+    the cost-ordered model list (heaviest first).  Plan text: comma-separated `MxK[@fraction]`; a part
+    takes `fraction` of the models (the last part takes the rest); `0x0` is the first-generation
+    one-CTA-per-model kernel.  CD_GROUP / CD_CLUSTER (or SGLM_CD_GROUP / SGLM_CD_CLUSTER) give a
+    one-part plan."""
+    import os
+    g = CD_GROUP if CD_GROUP is not None else os.environ.get("SGLM_CD_GROUP")
+    k = CD_CLUSTER if CD_CLUSTER is not None else os.environ.get("SGLM_CD_CLUSTER")
+    text = CD_PLAN if CD_PLAN is not None else os.environ.get("SGLM_CD_PLAN")
+    if g is not None or k is not None:
+        text = f"{int(1 if g is None else g)}x{int(1 if k is None else k)}"
+    if text is None:
+        text = _CD_DEFAULT_PLAN(C, n_models)
+    parts, r0 = [], 0
+    items = [t for t in text.split(",") if t]
+    for n, item in enumerate(items):
+        shape, _, frac = item.partition("@")
+        gg, kk = (int(v) for v in shape.split("x"))
+        r1 = n_models if (n == len(items) - 1 or not frac) else min(n_models, r0 + int(round(float(frac) * n_models)))
+        gg, kk = _cd_shape_ok(gg, kk, C)
+        parts.append((r0, r1, gg, kk))
+        r0 = r1
+    return parts
+
+
+def _CD_DEFAULT_PLAN(C, n_models):
+    # wide designs: pairs of models of one fold on 2-CTA clusters (measured best single shape,
+    # profiles/r1_cd_cluster.txt); narrow designs keep one CTA per model
+    return "2x2" if C > 1024 and n_models >= 16 else "0x0"
+
+
 def solve_models(models, C, do_screening=True):
     """Solve every model; returns (W [M, ldw] device, info [M,6] host, status list).
     ElasticNet/Lasso: one batched coordinate-descent launch.  Ridge/OLS: one Cholesky
@@ -350,9 +408,59 @@ def solve_models(models, C, do_screening=True):
             Wcd.copy_(torch.from_numpy(init))
         info_d = _zeros((n_slots, 6))
         if levels is None:
-            call("sglm_enet_cd_gram_f64", ptr(Qp), ptr(qp), ptr(dp), ptr(yy), ldq, C, ptr(pack_i[0]), ptr(pack_f[0]),
-                 ptr(pack_f[1]), ptr(pack_f[2]), ptr(pack_i[1]), n_slots, int(warm), int(do_screening),
-                 ptr(Wcd), ldw, ptr(info_d), stream_ptr())
+            # launch plan: consecutive parts of the cost-ordered model list, each with its own kernel shape
+            # (models per cluster x CTAs per cluster; 0x0 = first-generation kernel), each on its own
+            # stream so that clusters of heavy models and dense packs of light models share the SMs
+            parts = _cd_plan(C, n_slots)
+            tm_d = None
+            if any(g for _, _, g, _ in parts):
+                qh = np.array([p.Qc.data_ptr() for p in probs], dtype=np.uint64)
+                tm_h = np.zeros(len(probs) * nat.lib().sglm_enet_cd_cluster_tmap_bytes(), dtype=np.uint8)
+                rc_ = nat.lib().sglm_enet_cd_cluster_encode_tmaps(qh.ctypes.data_as(ctypes.c_void_p), len(probs), C,
+                                                                  ldq, tm_h.ctypes.data_as(ctypes.c_void_p))
+                if rc_ != 0:
+                    raise nat.SglmNativeError("cd tensor maps: " + nat.lib().sglm_last_error().decode())
+                tm_d = torch.from_numpy(tm_h).to("cuda")
+            main = torch.cuda.current_stream()
+            ready = torch.cuda.Event()
+            ready.record(main)
+            keep, side_done = [], []
+            for pi, (r0, r1, gsz, csz) in enumerate(parts):
+                if r1 <= r0:
+                    continue
+                st = main if pi == 0 else _side_stream(pi)
+                if st is not main:
+                    st.wait_event(ready)
+                with torch.cuda.stream(st):
+                    if gsz:
+                        # groups of `gsz` models of the same problem (neighbours in the cost order, so that
+                        # the members of a group run a similar number of sweeps), heaviest groups first
+                        by_prob = {}
+                        for r in range(r0, r1):
+                            by_prob.setdefault(slot_prob[r], []).append(r)
+                        groups = []
+                        for p_, rows_ in by_prob.items():
+                            for k in range(0, len(rows_), gsz):
+                                chunk = rows_[k:k + gsz]
+                                groups.append((chunk[0], p_, chunk + [-1] * (gsz - len(chunk))))
+                        groups.sort(key=lambda g: g[0])
+                        gp = _dev(np.array([g[1] for g in groups], dtype=np.int32), np.int32)
+                        gs = _dev(np.array([g[2] for g in groups], dtype=np.int32).reshape(-1), np.int32)
+                        keep += [gp, gs]
+                        call("sglm_enet_cd_cluster_f64", ptr(Qp), ptr(qp), ptr(dp), ptr(yy), ldq, C, ptr(gp), ptr(gs),
+                             ptr(pack_f[0]), ptr(pack_f[1]), ptr(pack_f[2]), ptr(pack_i[1]), len(groups), gsz, csz,
+                             int(warm) | (int(CD_DEBUG_TIMER) << 8), int(do_screening), ptr(Wcd), ldw, ptr(info_d),
+                             ptr(tm_d), stream_ptr())
+                    else:
+                        call("sglm_enet_cd_gram_f64", ptr(Qp), ptr(qp), ptr(dp), ptr(yy), ldq, C, ptr(pack_i[0][r0:]),
+                             ptr(pack_f[0][r0:]), ptr(pack_f[1][r0:]), ptr(pack_f[2][r0:]), ptr(pack_i[1][r0:]),
+                             r1 - r0, int(warm), int(do_screening), ptr(Wcd[r0:]), ldw, ptr(info_d[r0:]), stream_ptr())
+                    if st is not main:
+                        ev = torch.cuda.Event()
+                        ev.record(st)
+                        side_done.append(ev)
+            for ev in side_done:
+                main.wait_event(ev)
         else:
             pred_t = _dev(pred, np.int64)
             for k, (a, b) in enumerate(levels):
