@@ -330,9 +330,10 @@ def _cd_plan(C, n_models):
 
 
 def _CD_DEFAULT_PLAN(C, n_models):
-    # wide designs: pairs of models of one fold on 2-CTA clusters (measured best single shape,
+    # wide designs: the heaviest 30 % of the cost-ordered grid as groups of 4 models of one fold on 2-CTA
+    # clusters, the light rest concurrently on the one-CTA-per-model kernel (measured best,
     # profiles/r1_cd_cluster.txt); narrow designs keep one CTA per model
-    return "2x2" if C > 1024 and n_models >= 16 else "0x0"
+    return "4x2@0.3,0x0" if C > 1024 and n_models >= 16 else "0x0"
 
 
 def solve_models(models, C, do_screening=True):

@@ -122,14 +122,39 @@ def collect_timing():
     """-> {entry point: (calls, total ms)}; synchronises.  Clears the record."""
     import torch
     global _timing
+    global last_intervals
     out = {}
     if _timing:
         torch.cuda.synchronize()
+        ref = _timing[0][1]
+        last_intervals = []
         for name, e0, e1 in _timing:
             c, t = out.get(name, (0, 0.0))
             out[name] = (c + 1, t + e0.elapsed_time(e1))
+            a = ref.elapsed_time(e0)
+            last_intervals.append((name, a, a + e0.elapsed_time(e1)))
         _timing = []
     return out
+
+
+last_intervals = []     # (entry point, start ms, end ms) of the calls of the last collect_timing(), relative to its first call
+
+
+def union_ms(names):
+    """Total time covered by the calls of `names` in the last collected record (calls on different
+    streams overlap: the coordinate-descent parts of one grid run concurrently)."""
+    iv = sorted((a, b) for n, a, b in last_intervals if n in names)
+    total, cur_a, cur_b = 0.0, None, None
+    for a, b in iv:
+        if cur_b is None or a > cur_b:
+            if cur_b is not None:
+                total += cur_b - cur_a
+            cur_a, cur_b = a, b
+        else:
+            cur_b = max(cur_b, b)
+    if cur_b is not None:
+        total += cur_b - cur_a
+    return total
 
 
 last_tc_plan = None     # {S, n_pos, tiles, segs} of the most recent tensor-core Gram (bench.py reads it)

@@ -734,22 +734,22 @@ static int launch_a(const Args &a) {
 }
 
 // Panel shapes (panel warps NB, 16-byte chunks per thread CH, rows per load group RG, min CTAs per SM).
-// The chunk loop of the panel is generic, so every shape is valid for every C.  Default: follow the
-// number of columns a CTA owns (ceil(C/32/K) blocks of 16 double2), sized for two resident CTAs per SM
-// (while one cluster waits on a hand-over its SM still has work); `variant` (tuning switch
-// SGLM_CDC_VARIANT) forces one shape — measurements in profiles/r1_cd_cluster.txt.
+// The chunk loop of the panel is generic, so every shape is valid for every C.  The panel is bound by
+// latency x bytes in flight (RG*CH 16-byte loads per thread): a CTA that owns many columns gets the
+// register budget of a whole SM (8 loads in flight per thread, measured best: profiles/r1_cd_cluster.txt),
+// narrow slices are sized for two resident CTAs per SM.  `variant` (tuning switch SGLM_CDC_VARIANT)
+// forces one shape.
 template <int M, int K>
 static int launch_sized(const Args &a) {
     const int own2 = ((a.C + 31) / 32 + K - 1) / K * 16;
     switch (a.variant) {
         case 1: return launch_a<M, K, 8, 1, 4, 1>(a);
-        case 2: return launch_a<M, K, 4, 1, 4, 2>(a);
-        case 3: return launch_a<M, K, 8, 2, 4, 1>(a);
+        case 2: return launch_a<M, K, 8, 2, 2, 2>(a);
         default: break;
     }
     if (own2 <= 128) return launch_a<M, K, 4, 1, (M >= 4 ? 4 : 8), 2>(a);
     if (own2 <= 256) return launch_a<M, K, 4, 2, (M >= 4 ? 2 : 4), 2>(a);
-    return launch_a<M, K, 8, 2, 2, 2>(a);
+    return launch_a<M, K, 8, 2, 4, 1>(a);
 }
 
 template <int M>

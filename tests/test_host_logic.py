@@ -148,3 +148,26 @@ def test_shard_indices_partition():
     assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
     heavy = int(np.argmax(cost))
     assert heavy in parts[0]                                     # most expensive set dealt first
+
+
+def test_cd_launch_plan_parsing():
+    """Launch plan of the coordinate-descent grid (host logic only; the library is loaded to ask which
+    cluster shapes are compiled in)."""
+    import _engine as eng
+    old = (eng.CD_PLAN, eng.CD_GROUP, eng.CD_CLUSTER)
+    try:
+        eng.CD_GROUP = eng.CD_CLUSTER = None
+        eng.CD_PLAN = "4x2@0.3,0x0"
+        assert eng._cd_plan(2000, 1500) == [(0, 450, 4, 2), (450, 1500, 0, 0)]
+        eng.CD_PLAN = "2x8@0.1,4x4@0.2,1x1"
+        assert eng._cd_plan(2000, 1000) == [(0, 100, 2, 8), (100, 300, 4, 4), (300, 1000, 1, 1)]
+        eng.CD_PLAN = "4x8"
+        assert eng._cd_plan(96, 10) == [(0, 10, 4, 1)]           # 3 coordinate blocks cannot feed 8 CTAs
+        eng.CD_PLAN = None
+        assert eng._cd_plan(410, 1500) == [(0, 1500, 0, 0)]       # narrow design: one CTA per model
+        assert eng._cd_plan(2000, 1500)[0][2:] == (4, 2)
+        eng.CD_PLAN = "3x2"
+        with pytest.raises(Exception):
+            eng._cd_plan(2000, 10)
+    finally:
+        eng.CD_PLAN, eng.CD_GROUP, eng.CD_CLUSTER = old
