@@ -41,6 +41,7 @@ namespace sglm {
 namespace cdc {
 
 constexpr int RING = 16;   // records in flight per cluster (flow-controlled by completion counters)
+constexpr int RS = 40;     // doubles per (record, model): 32 deltas + zeros that partial load groups read
 
 struct Layout {
     int NBLK, BPC, CoP;
@@ -57,7 +58,7 @@ __host__ __device__ inline Layout make_layout(int M, int K, int NB, int C) {
     L.Qw = o;     o += (size_t)M * L.CoP * 8;
     L.blk = o;    o += (size_t)4 * 1024 * 8;          // [buf 2][diag, off][32][32]
     L.qd = o;     o += (size_t)2 * 64 * 8;            // [buf 2][q, diag][32]
-    L.rdelta = o; o += (size_t)RING * M * 32 * 8;
+    L.rdelta = o; o += (size_t)(RING * M + 1) * RS * 8;   // + one all-zero page (models that did not move)
     L.rmask = o;  o += (size_t)RING * M * 8;
     L.full = o;   o += (size_t)RING * 8;
     L.bbar = o;   o += (size_t)2 * 8;               // sub-block buffers landed
@@ -199,9 +200,15 @@ enet_cd_cluster_kernel(const double *const *__restrict__ prob_Q, const double *c
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned rank = (K > 1) ? cluster_rank() : 0u;
     const int grp = blockIdx.x / K;
-    const bool is_seq = warp < M;
-    const int m = warp;                       // model slot of a register warp
-    const int pw = warp - M, bt = tid - M * 32;
+    // Warp roles.  The register warps sit on warp ids 0, 4, 8, ... — all on the same SM sub-partition — when the
+    // CTA has enough warps: their dependent chains (one shuffle and three FP64 operations per coordinate) then
+    // do not queue behind the panel warps' loads and FMAs in the same scheduler (measured: the register phase
+    // took 2.5 us per block next to busy panel warps against 1.56 us alone, profiles/r1_cd_cluster.txt).
+    constexpr bool SPREAD = 4 * (M - 1) < M + NB;
+    const bool is_seq = SPREAD ? ((warp & 3) == 0 && (warp >> 2) < M) : (warp < M);
+    const int m = SPREAD ? (warp >> 2) : warp;            // model slot of a register warp
+    const int pw = SPREAD ? warp - min(M, (warp + 3) >> 2) : warp - M;
+    const int bt = pw * 32 + lane;
     const int NBLK = L.NBLK, CoP = L.CoP;
     const int blo = min(NBLK, (int)rank * L.BPC), bhi = min(NBLK, blo + L.BPC);
     const int col0 = blo * 32;
@@ -228,6 +235,7 @@ enet_cd_cluster_kernel(const double *const *__restrict__ prob_Q, const double *c
         p[6] = 0.0; p[7] = 0.0;
     }
     for (int i = tid; i < M * CoP; i += NT) { w_s[i] = 0.0; Qw_s[i] = 0.0; }
+    for (int i = tid; i < (RING * M + 1) * RS; i += NT) rdelta[i] = 0.0;      // entries 32.. of every page stay zero
     for (int i = tid; i < NB; i += NT) pdone[i] = 0u;
     for (int i = tid; i < K * NB; i += NT) ccnt[i] = 0u;
     if (tid == 0) {
@@ -560,7 +568,7 @@ enet_cd_cluster_kernel(const double *const *__restrict__ prob_Q, const double *c
                             if (!__all_sync(0xffffffffu, ok)) { ok = false; __nanosleep(64); } else ok = true;
                         } while (!ok);
                     }
-                    const unsigned la_d = s_addr(rdelta + (slot * M + m) * 32 + lane);
+                    const unsigned la_d = s_addr(rdelta + (slot * M + m) * RS + lane);
                     const unsigned la_m = s_addr(rmask + slot * M + m);
                     const unsigned la_b = s_addr(fullb + slot);
 #pragma unroll
@@ -605,7 +613,11 @@ enet_cd_cluster_kernel(const double *const *__restrict__ prob_Q, const double *c
                 for (int mm = 0; mm < M; ++mm) { mk[mm] = (unsigned)rmask[slot * M + mm]; um |= mk[mm]; }
                 if (um) {
                     const double2 *Q2 = reinterpret_cast<const double2 *>(Q + (long long)(b << 5) * ldq + col0);
-                    const double *dl = rdelta + slot * M * 32;
+                    // A model that moved sent all 32 deltas (exact zeros for the rows that stayed), a model that
+                    // did not move reads the zero page: no per-row selects in the loop below.
+                    const double *dlm[M];
+#pragma unroll
+                    for (int mm = 0; mm < M; ++mm) dlm[mm] = rdelta + (mk[mm] ? (slot * M + mm) : RING * M) * RS;
                     for (int c0 = bt; c0 < Co2; c0 += NTB * CH) {
                         double2 acc[M][CH];
                         bool okc[CH];
@@ -623,12 +635,11 @@ enet_cd_cluster_kernel(const double *const *__restrict__ prob_Q, const double *c
 #pragma unroll
                             for (int g = 0; g < RG; ++g) {
                                 const bool has = rem != 0u;
-                                const int i = has ? (__ffs(rem) - 1) : 0;
+                                const int i = has ? (__ffs(rem) - 1) : 32;    // 32: zero delta, row 0 of the block
                                 rem &= rem - 1;                               // (0 & -1) stays 0
 #pragma unroll
-                                for (int mm = 0; mm < M; ++mm)
-                                    d[g][mm] = (has && ((mk[mm] >> i) & 1u)) ? dl[mm * 32 + i] : 0.0;
-                                const double2 *row = Q2 + (long long)i * ld2 + c0;
+                                for (int mm = 0; mm < M; ++mm) d[g][mm] = dlm[mm][i];
+                                const double2 *row = Q2 + (long long)(i & 31) * ld2 + c0;
 #pragma unroll
                                 for (int u = 0; u < CH; ++u)
                                     v[g][u] = okc[u] ? __ldg(row + u * NTB) : make_double2(0.0, 0.0);
@@ -735,10 +746,9 @@ static int launch_a(const Args &a) {
 
 // Panel shapes (panel warps NB, 16-byte chunks per thread CH, rows per load group RG, min CTAs per SM).
 // The chunk loop of the panel is generic, so every shape is valid for every C.  The panel is bound by
-// latency x bytes in flight (RG*CH 16-byte loads per thread): a CTA that owns many columns gets the
-// register budget of a whole SM (8 loads in flight per thread, measured best: profiles/r1_cd_cluster.txt),
-// narrow slices are sized for two resident CTAs per SM.  `variant` (tuning switch SGLM_CDC_VARIANT)
-// forces one shape.
+// latency x bytes in flight (RG*CH 16-byte loads per thread), so a CTA gets the register budget of a
+// whole SM: 8 loads in flight per thread, one thread per 16-byte column chunk where the slice is narrow
+// (measured: profiles/r1_cd_cluster.txt).  `variant` (tuning switch SGLM_CDC_VARIANT) forces one shape.
 template <int M, int K>
 static int launch_sized(const Args &a) {
     const int own2 = ((a.C + 31) / 32 + K - 1) / K * 16;
@@ -747,8 +757,8 @@ static int launch_sized(const Args &a) {
         case 2: return launch_a<M, K, 8, 2, 2, 2>(a);
         default: break;
     }
-    if (own2 <= 128) return launch_a<M, K, 4, 1, (M >= 4 ? 4 : 8), 2>(a);
-    if (own2 <= 256) return launch_a<M, K, 4, 2, (M >= 4 ? 2 : 4), 2>(a);
+    if (own2 <= 128) return launch_a<M, K, 4, 1, 8, 1>(a);
+    if (own2 <= 256) return launch_a<M, K, 8, 1, 8, 1>(a);
     return launch_a<M, K, 8, 2, 4, 1>(a);
 }
 
