@@ -309,6 +309,8 @@ def main():
     CD = "sglm_enet_cd (cluster + per-model parts, concurrent)" if len(cd_parts) > 1 else next(iter(cd_parts), cd_names[0])
     if cd_parts:
         k_ms[CD] = nat.union_ms(cd_names) / args.steps
+    if "sglm_gram_tc_cells_f64" in k_ms:          # the Gram over the disjoint cells of the row sets (same statistics)
+        k_ms["sglm_gram_tc_f64"] = k_ms.pop("sglm_gram_tc_cells_f64")
     dominant = max(k_ms, key=k_ms.get)
     alg = {
         "sglm_timeshift_f64_ranged": ("hbm", 8.0 * args.T * args.P + 8.0 * args.T * C),

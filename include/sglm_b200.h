@@ -120,6 +120,18 @@ int sglm_gram_tc_f64(const double *X, int64_t ldx, const double *Y, int64_t ldy,
                      int64_t ldg, void *workspace, size_t workspace_bytes, int32_t use_check_gemm,
                      void *stream);
 
+/* The same statistics from DISJOINT cells.  The row sets of a CV grid overlap (the full data contain every
+ * test fold, random folds intersect); the partition they induce has n_cells cells, the int8 GEMM runs once over
+ * every row (not once per set), and the Gram of output set o is the exact integer sum of the cells with
+ * member_host[o * n_cells + c] != 0.  rows / cell_rows_host as rows / set_rows_host above; G holds n_out sets. */
+size_t sglm_gram_tc_cells_workspace_bytes(int32_t n_aug, const int32_t *colS_host, int32_t n_cells,
+                                          const int64_t *cell_rows_host, int32_t n_out);
+int sglm_gram_tc_cells_f64(const double *X, int64_t ldx, const double *Y, int64_t ldy, int32_t n_y, int64_t T,
+                           int32_t C, const int32_t *colE, const int32_t *colS, const int32_t *colS_host,
+                           int32_t n_cells, const int64_t *cell_rows_host, const int64_t *rows, int32_t n_out,
+                           const int32_t *member_host, double *G, int64_t ldg, void *workspace,
+                           size_t workspace_bytes, int32_t use_check_gemm, void *stream);
+
 /* Index lists -> per-row multiplicities: counts[idx[i]] += 1 (the fold row sets of
  * backend/sglm_cv.py:106-110, X[idx_train,:] / X[idx_test,:]).  counts must be zeroed. */
 int sglm_index_counts_f64(const int64_t *idx, int64_t n_idx, double *counts, int64_t T,

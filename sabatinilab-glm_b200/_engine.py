@@ -194,10 +194,16 @@ def suffstats_tc(Xd, Yd, set_rows, check_gemm=False):
     if host[-1] != 0:
         raise ValueError("Input contains NaN, infinity or a value too large for dtype('float64').")
     colS_h = np.ascontiguousarray(host[:-1], dtype=np.int32)
-    sizes = np.ascontiguousarray([T if r is None else int(r.numel()) for r in set_rows], dtype=np.int64)
+    cells = None if TC_CELLS is False else _row_cells(set_rows, T)
+    if cells is None:
+        lists = [torch.arange(T, dtype=torch.int64, device="cuda") if r is None else r.to(torch.int64) for r in set_rows]
+        member = None
+    else:
+        lists, member = cells
+    n_lists = len(lists)
+    sizes = np.ascontiguousarray([int(r.numel()) for r in lists], dtype=np.int64)
     parts = []
-    for r, n in zip(set_rows, sizes):
-        body = torch.arange(T, dtype=torch.int64, device="cuda") if r is None else r.to(torch.int64)
+    for body, n in zip(lists, sizes):
         pad = (-int(n)) % 128
         parts.append(body)
         if pad:
@@ -205,22 +211,72 @@ def suffstats_tc(Xd, Yd, set_rows, check_gemm=False):
     rows = torch.cat(parts) if parts else torch.empty(0, dtype=torch.int64, device="cuda")
     if rows.numel() == 0:
         rows = torch.full((128,), -1, dtype=torch.int64, device="cuda")
-    ws_bytes = nat.lib().sglm_gram_tc_workspace_bytes(n_aug, colS_h.ctypes.data_as(ctypes.c_void_p), n_sets,
-                                                      sizes.ctypes.data_as(ctypes.c_void_p))
+    colS_p, sizes_p = colS_h.ctypes.data_as(ctypes.c_void_p), sizes.ctypes.data_as(ctypes.c_void_p)
+    if member is None:
+        ws_bytes = nat.lib().sglm_gram_tc_workspace_bytes(n_aug, colS_p, n_lists, sizes_p)
+    else:
+        ws_bytes = nat.lib().sglm_gram_tc_cells_workspace_bytes(n_aug, colS_p, n_lists, sizes_p, n_sets)
     if ws_bytes == 0:
         raise nat.SglmNativeError("gram_tc: invalid plan")
     info = np.zeros(4, dtype=np.int64)
-    nat.lib().sglm_gram_tc_plan_info(n_aug, colS_h.ctypes.data_as(ctypes.c_void_p), n_sets,
-                                     sizes.ctypes.data_as(ctypes.c_void_p), info.ctypes.data_as(ctypes.c_void_p))
+    nat.lib().sglm_gram_tc_plan_info(n_aug, colS_p, n_lists, sizes_p, info.ctypes.data_as(ctypes.c_void_p))
     nat.last_tc_plan = dict(S=int(info[0]), n_pos=int(info[1]), tiles=int(info[2]), k_parts=int(info[3]),
-                            planes=int(colS_h.sum()), n_aug=n_aug)
+                            planes=int(colS_h.sum()), n_aug=n_aug, row_lists=n_lists, cells=member is not None)
     raw = torch.empty(ws_bytes + 1024, dtype=torch.uint8, device="cuda")
     off = (-raw.data_ptr()) % 1024
     G = _zeros((n_sets, n_aug, ldg))
-    call("sglm_gram_tc_f64", ptr(Xd), row_stride(Xd), ptr(Yd), row_stride(Yd), n_y, T, C, ptr(colE), ptr(colS),
-         colS_h.ctypes.data_as(ctypes.c_void_p), n_sets, sizes.ctypes.data_as(ctypes.c_void_p), ptr(rows), ptr(G), ldg,
-         ctypes.c_void_p(raw.data_ptr() + off), ws_bytes, int(bool(check_gemm)), stream_ptr())
+    if member is None:
+        call("sglm_gram_tc_f64", ptr(Xd), row_stride(Xd), ptr(Yd), row_stride(Yd), n_y, T, C, ptr(colE), ptr(colS),
+             colS_p, n_lists, sizes_p, ptr(rows), ptr(G), ldg, ctypes.c_void_p(raw.data_ptr() + off), ws_bytes,
+             int(bool(check_gemm)), stream_ptr())
+    else:
+        member = np.ascontiguousarray(member, dtype=np.int32)
+        call("sglm_gram_tc_cells_f64", ptr(Xd), row_stride(Xd), ptr(Yd), row_stride(Yd), n_y, T, C, ptr(colE),
+             ptr(colS), colS_p, n_lists, sizes_p, ptr(rows), n_sets, member.ctypes.data_as(ctypes.c_void_p), ptr(G), ldg,
+             ctypes.c_void_p(raw.data_ptr() + off), ws_bytes, int(bool(check_gemm)), stream_ptr())
     return G, colS_h
+
+
+TC_CELLS = None      # False: one GEMM pass per row set (no cell decomposition); None: decompose when it pays
+_MAX_CELLS = 64
+
+
+def _row_cells(set_rows, T):
+    """Disjoint cells of the partition of the rows induced by overlapping row sets.
+    set_rows: None (all rows) or sorted duplicate-free int64 CUDA tensors.  Returns
+    ([rows of cell c], member[n_sets][n_cells]) or None when the decomposition does not pay
+    (no overlap, too many sets or cells).  The full data of a CV grid contain every test fold and
+    random folds (GroupShuffleSplit, backend/sglm_pp.py:262-263) intersect: the cells are visited
+    once by the GEMM, the sets are integer sums of cell Grams."""
+    torch = nat.require_cuda()
+    listed = [i for i, r in enumerate(set_rows) if r is not None]
+    if not listed or len(listed) > 60 or len(set_rows) < 2:
+        return None
+    any_all = len(listed) < len(set_rows)
+    sig = torch.zeros(T, dtype=torch.int64, device="cuda")
+    for bit, i in enumerate(listed):
+        sig[set_rows[i].to(torch.int64)] += (1 << bit)
+    order = torch.argsort(sig, stable=True)
+    uniq, counts = torch.unique_consecutive(sig[order], return_counts=True)
+    if uniq.numel() > _MAX_CELLS + 1:
+        return None
+    host = torch.stack([uniq, counts]).cpu().numpy()
+    uniq_h, counts_h = host[0], host[1]
+    total_listed = sum(int(set_rows[i].numel()) for i in listed) + (T if any_all else 0) * (len(set_rows) - len(listed))
+    cell_rows = int(counts_h.sum()) if any_all else int(counts_h[uniq_h != 0].sum())
+    if cell_rows >= total_listed:             # disjoint sets: nothing to share
+        return None
+    lists, member_cols = [], []
+    start = 0
+    bit_of = {i: b for b, i in enumerate(listed)}
+    for u, n in zip(uniq_h, counts_h):
+        n = int(n)
+        if u != 0 or any_all:
+            lists.append(order[start:start + n])
+            member_cols.append([1 if r is None else int((int(u) >> bit_of[i]) & 1) for i, r in enumerate(set_rows)])
+        start += n
+    member = np.array(member_cols, dtype=np.int32).T          # [n_sets][n_cells]
+    return lists, member
 
 
 class Problem:

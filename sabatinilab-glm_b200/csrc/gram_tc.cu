@@ -247,10 +247,17 @@ tc_gram_i8_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restri
     const int2 tile = tiles[item % n_tiles];
     const int part = item / n_tiles;
     const int m0 = tile.x * TC_BM, n0 = tile.y * TC_BN;
-    // this item's share of segment sg: K blocks [lo, hi)
-    auto seg_range = [&](const TcSeg &sg, int &lo, int &hi) {
-        lo = sg.kb0 + (int)(((long long)sg.n_kb * part) / n_parts);
-        hi = sg.kb0 + (int)(((long long)sg.n_kb * (part + 1)) / n_parts);
+    // This item's share of the K space: part p owns a CONTIGUOUS range of the concatenated K blocks of all
+    // segments (so a tile is drained once per row set plus once per part boundary, however many row sets
+    // there are).  seg_range gives its K blocks [lo, hi) inside segment sgi; `before` = K blocks of the
+    // segments ahead of it.
+    long long total_kb = 0;
+    for (int sgi = 0; sgi < n_segs; ++sgi) total_kb += segs[sgi].n_kb;
+    const long long part_lo = total_kb * part / n_parts, part_hi = total_kb * (part + 1) / n_parts;
+    auto seg_range = [&](const TcSeg &sg, long long before, int &lo, int &hi) {
+        const long long a = max(part_lo, before), b = min(part_hi, before + sg.n_kb);
+        lo = sg.kb0 + (int)(a - before);
+        hi = (b > a) ? sg.kb0 + (int)(b - before) : lo;
     };
 
     if (threadIdx.x == 0) {
@@ -272,9 +279,11 @@ tc_gram_i8_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restri
         // ===== TMA producer (one elected lane)
         if (lane == 0) {
             int it = 0;
+            long long before = 0;
             for (int sgi = 0; sgi < n_segs; ++sgi) {
                 int lo, hi;
-                seg_range(segs[sgi], lo, hi);
+                seg_range(segs[sgi], before, lo, hi);
+                before += segs[sgi].n_kb;
                 for (int kb = lo; kb < hi; ++kb, ++it) {
                     const int st = it % TC_STAGES;
                     const uint32_t ph = (it / TC_STAGES) & 1;
@@ -294,9 +303,11 @@ tc_gram_i8_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restri
         if (lane == 0) {
             constexpr uint32_t idesc = tc_idesc_i8();
             int it = 0, drained = 0;
+            long long before = 0;
             for (int sgi = 0; sgi < n_segs; ++sgi) {
                 int lo, hi;
-                seg_range(segs[sgi], lo, hi);
+                seg_range(segs[sgi], before, lo, hi);
+                before += segs[sgi].n_kb;
                 if (hi <= lo) continue;
                 if (drained > 0) { mbar_wait(tmem_empty, (drained - 1) & 1); tc_fence_after(); }
                 for (int kb = lo; kb < hi; ++kb, ++it) {
@@ -324,10 +335,12 @@ tc_gram_i8_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restri
         const int q = warp & 3;                                    // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;
         int drained = 0;
+        long long before = 0;
         for (int sgi = 0; sgi < n_segs; ++sgi) {
             const TcSeg sg = segs[sgi];
             int lo, hi;
-            seg_range(sg, lo, hi);
+            seg_range(sg, before, lo, hi);
+            before += sg.n_kb;
             if (hi <= lo) continue;
             mbar_wait(tmem_full, drained & 1);
             tc_fence_after();
@@ -392,6 +405,23 @@ tc_gram_i8_check_kernel(const int8_t *__restrict__ At, long long ld_at, const in
             }
             acc += part;
             SG[((long long)sg.set * S + m) * S + n] += acc;       // SG zeroed by the host; one thread per element
+        }
+    }
+}
+
+// ------------------------------------------------------------------ cells -> row sets (exact integer sums)
+// SGout[o][e] = sum over the cells c with member[o * n_cells + c] != 0 of SG[c][e]: the row sets of a CV grid
+// overlap (the full data contain every test fold, random folds intersect), so the GEMM runs once over the
+// disjoint CELLS of the partition they induce and the Gram of each set is the sum of its cells' Grams.
+__global__ void __launch_bounds__(256)
+tc_cell_sum_kernel(const long long *__restrict__ SG, long long n_elem, int n_cells, const int *__restrict__ member,
+                   int n_out, long long *__restrict__ SGout) {
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < n_elem; e += (long long)gridDim.x * 256) {
+        for (int o = 0; o < n_out; ++o) {
+            long long acc = 0;
+            for (int c = 0; c < n_cells; ++c)
+                if (member[o * n_cells + c]) acc += SG[(long long)c * n_elem + e];
+            SGout[(long long)o * n_elem + e] = acc;
         }
     }
 }
@@ -534,13 +564,17 @@ static void tc_make_plan(int n_aug, const int *colS, int n_sets, const long long
 
 static inline size_t tc_align(size_t x) { return (x + 1023) & ~(size_t)1023; }
 
-struct TcLayout { size_t off_at, off_sg, off_plane, off_tiles, off_segs, total; };
+struct TcLayout { size_t off_at, off_sg, off_sgout, off_member, off_plane, off_tiles, off_segs, total; };
 
-static TcLayout tc_layout(const TcPlan &p) {
+// n_out > 0: the plan's sets are cells and n_out row sets are summed from them (extra int64 Grams + the
+// membership table)
+static TcLayout tc_layout(const TcPlan &p, int n_out = 0) {
     TcLayout L;
     size_t o = 0;
     L.off_at = o; o += tc_align((size_t)p.S * p.n_pos);
     L.off_sg = o; o += tc_align((size_t)p.n_sets * p.S * p.S * sizeof(long long));
+    L.off_sgout = o; o += tc_align((size_t)n_out * p.S * p.S * sizeof(long long));
+    L.off_member = o; o += tc_align((size_t)n_out * p.n_sets * sizeof(int));
     L.off_plane = o; o += tc_align(p.plane_row.size() * sizeof(int));
     L.off_tiles = o; o += tc_align(p.tiles.size() * sizeof(int2));
     L.off_segs = o; o += tc_align(p.segs.size() * sizeof(TcSeg));
@@ -596,11 +630,47 @@ extern "C" int sglm_gram_tc_plan_info(int32_t n_aug, const int32_t *colS_host, i
 // Pass 2: slices, int8 tcgen05 GEMM, combine.  rows: device int64 [sum of 128-padded set sizes]
 // (concatenated row lists of the sets, -1 = padding), built by the caller in set order.
 // use_check_gemm != 0 runs the CUDA-core integer GEMM instead of tcgen05 (cross-check, small sizes).
+static int gram_tc_run(const double *X, int64_t ldx, const double *Y, int64_t ldy, int32_t n_y, int64_t T,
+                       int32_t C, const int32_t *colE, const int32_t *colS, const int32_t *colS_host,
+                       int32_t n_sets, const int64_t *set_rows_host, const int64_t *rows, int32_t n_out,
+                       const int32_t *member_host, double *G, int64_t ldg, void *workspace, size_t workspace_bytes,
+                       int32_t use_check_gemm, void *stream);
+
 extern "C" int sglm_gram_tc_f64(const double *X, int64_t ldx, const double *Y, int64_t ldy, int32_t n_y, int64_t T,
                                 int32_t C, const int32_t *colE, const int32_t *colS, const int32_t *colS_host,
                                 int32_t n_sets, const int64_t *set_rows_host, const int64_t *rows, double *G,
                                 int64_t ldg, void *workspace, size_t workspace_bytes, int32_t use_check_gemm,
                                 void *stream) {
+    return gram_tc_run(X, ldx, Y, ldy, n_y, T, C, colE, colS, colS_host, n_sets, set_rows_host, rows, 0, nullptr, G, ldg,
+                       workspace, workspace_bytes, use_check_gemm, stream);
+}
+
+extern "C" size_t sglm_gram_tc_cells_workspace_bytes(int32_t n_aug, const int32_t *colS_host, int32_t n_cells,
+                                                     const int64_t *cell_rows_host, int32_t n_out) {
+    if (n_aug <= 0 || n_cells <= 0 || n_out <= 0 || !colS_host || !cell_rows_host) return 0;
+    TcPlan p;
+    tc_make_plan(n_aug, colS_host, n_cells, (const long long *)cell_rows_host, p);
+    return tc_layout(p, n_out).total;
+}
+
+// Same statistics from DISJOINT cells: rows = concatenated (128-padded) row lists of the n_cells cells,
+// member_host[o * n_cells + c] != 0 when cell c belongs to output row set o; G holds the n_out sets.
+extern "C" int sglm_gram_tc_cells_f64(const double *X, int64_t ldx, const double *Y, int64_t ldy, int32_t n_y,
+                                      int64_t T, int32_t C, const int32_t *colE, const int32_t *colS,
+                                      const int32_t *colS_host, int32_t n_cells, const int64_t *cell_rows_host,
+                                      const int64_t *rows, int32_t n_out, const int32_t *member_host, double *G,
+                                      int64_t ldg, void *workspace, size_t workspace_bytes, int32_t use_check_gemm,
+                                      void *stream) {
+    SGLM_CHECK_ARG(n_out >= 1 && member_host, SGLM_E_INVALID_ARG, "gram_tc_cells: membership table missing");
+    return gram_tc_run(X, ldx, Y, ldy, n_y, T, C, colE, colS, colS_host, n_cells, cell_rows_host, rows, n_out,
+                       member_host, G, ldg, workspace, workspace_bytes, use_check_gemm, stream);
+}
+
+static int gram_tc_run(const double *X, int64_t ldx, const double *Y, int64_t ldy, int32_t n_y, int64_t T,
+                       int32_t C, const int32_t *colE, const int32_t *colS, const int32_t *colS_host,
+                       int32_t n_sets, const int64_t *set_rows_host, const int64_t *rows, int32_t n_out,
+                       const int32_t *member_host, double *G, int64_t ldg, void *workspace, size_t workspace_bytes,
+                       int32_t use_check_gemm, void *stream) {
     const int n_aug = C + n_y + 1;
     SGLM_CHECK_ARG(T >= 0 && C >= 0 && n_y >= 0 && n_sets >= 1 && ldx >= C && ldy >= n_y && ldg >= n_aug, SGLM_E_SHAPE,
                    "gram_tc: bad shape");
@@ -609,7 +679,7 @@ extern "C" int sglm_gram_tc_f64(const double *X, int64_t ldx, const double *Y, i
     SGLM_CHECK_ARG(((uintptr_t)workspace & 1023) == 0, SGLM_E_ALIGN, "gram_tc: workspace must be 1024-byte aligned");
     TcPlan p;
     tc_make_plan(n_aug, colS_host, n_sets, (const long long *)set_rows_host, p);
-    const TcLayout L = tc_layout(p);
+    const TcLayout L = tc_layout(p, n_out);
     SGLM_CHECK_ARG(workspace_bytes >= L.total, SGLM_E_WORKSPACE, "gram_tc: workspace too small (%zu < %zu)",
                    workspace_bytes, L.total);
     SGLM_CHECK_ARG(p.n_pos < 0x7fffffffLL && p.S < 0x7fffffffLL, SGLM_E_SHAPE, "gram_tc: problem too large");
@@ -636,6 +706,10 @@ extern "C" int sglm_gram_tc_f64(const double *X, int64_t ldx, const double *Y, i
     SGLM_CUDA_OK(cudaMemcpyAsync(d_plane, p.plane_row.data(), p.plane_row.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     SGLM_CUDA_OK(cudaMemcpyAsync(d_tiles, p.tiles.data(), p.tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
     SGLM_CUDA_OK(cudaMemcpyAsync(d_segs, p.segs.data(), p.segs.size() * sizeof(TcSeg), cudaMemcpyHostToDevice, st));
+    long long *SGout = (long long *)(ws + L.off_sgout);
+    int *d_member = (int *)(ws + L.off_member);
+    if (n_out > 0)
+        SGLM_CUDA_OK(cudaMemcpyAsync(d_member, member_host, (size_t)n_out * n_sets * sizeof(int), cudaMemcpyHostToDevice, st));
     SGLM_CUDA_OK(cudaStreamSynchronize(st));        // the pageable host vectors above die with this frame
 
     dim3 sgrid((unsigned)(p.n_pos / 128), (unsigned)ceil_div(n_aug, 32));
@@ -665,8 +739,16 @@ extern "C" int sglm_gram_tc_f64(const double *X, int64_t ldx, const double *Y, i
                                                                         (int)p.segs.size(), SG, p.S);
         SGLM_LAUNCH_OK("tc_gram_i8_kernel");
     }
-    dim3 cgrid((unsigned)std::min(ceil_div(n_aug, 256), 32), (unsigned)n_aug, (unsigned)n_sets);
-    tc_combine_kernel<<<cgrid, 256, 0, st>>>(SG, p.S, colE, colS, d_plane, n_aug, G, ldg);
+    const long long *SGfin = SG;
+    int n_fin = n_sets;
+    if (n_out > 0) {
+        tc_cell_sum_kernel<<<sm_count() * 8, 256, 0, st>>>(SG, p.S * p.S, n_sets, d_member, n_out, SGout);
+        SGLM_LAUNCH_OK("tc_cell_sum_kernel");
+        SGfin = SGout;
+        n_fin = n_out;
+    }
+    dim3 cgrid((unsigned)std::min(ceil_div(n_aug, 256), 32), (unsigned)n_aug, (unsigned)n_fin);
+    tc_combine_kernel<<<cgrid, 256, 0, st>>>(SGfin, p.S, colE, colS, d_plane, n_aug, G, ldg);
     SGLM_LAUNCH_OK("tc_combine_kernel");
     return SGLM_OK;
 }

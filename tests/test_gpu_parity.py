@@ -221,6 +221,43 @@ def test_tensor_core_gram_matches_fp64(T, C, check):
         assert torch.equal(G, G2)
 
 
+def test_tensor_core_gram_cell_decomposition_is_exact():
+    """Overlapping row sets (full data + random, intersecting folds): the GEMM over the disjoint cells of
+    the induced partition + integer cell sums must give the SAME bits as one GEMM pass per set, for the
+    tcgen05 kernel and for the CUDA-core check GEMM."""
+    T, C = 6000, 150
+    X = _mixed_design(T, C, 5)
+    rng = np.random.default_rng(8)
+    y = rng.standard_normal((T, 1))
+    Xd, Yd = torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda()
+    groups = np.arange(T) // 50
+    sets = [None]
+    for f in range(4):
+        pick = rng.permutation(groups.max() + 1)[: (groups.max() + 1) // 4]           # random 25 % of the groups
+        sets.append(torch.from_numpy(np.flatnonzero(np.isin(groups, pick))).cuda())
+    assert eng._row_cells(sets, T) is not None
+    old = eng.TC_CELLS
+    try:
+        eng.TC_CELLS = False
+        G_sets, _ = eng.suffstats_tc(Xd, Yd, sets)
+        assert not nat.last_tc_plan["cells"]
+        eng.TC_CELLS = None
+        G_cells, _ = eng.suffstats_tc(Xd, Yd, sets)
+        assert nat.last_tc_plan["cells"] and nat.last_tc_plan["n_pos"] < 1.2 * T
+        G_check, _ = eng.suffstats_tc(Xd, Yd, sets, check_gemm=True)
+    finally:
+        eng.TC_CELLS = old
+    assert torch.equal(G_sets, G_cells) and torch.equal(G_cells, G_check)
+    # disjoint sets (a K-fold partition without the full data): nothing to share, the per-set path is taken
+    assert eng._row_cells([sets[1], torch.from_numpy(np.setdiff1d(np.arange(T), sets[1].cpu().numpy())).cuda()], T) is None
+    Z = np.hstack([X, y, np.ones((T, 1))])
+    for s_i, rows in enumerate(sets):
+        Zs = Z if rows is None else Z[rows.cpu().numpy()]
+        want = Zs.T @ Zs
+        got = G_cells[s_i, :, :C + 2].cpu().numpy()
+        assert np.max(np.abs(got - want)) <= 1e-12 * np.max(np.abs(want))
+
+
 def test_tensor_core_gram_rejects_nan():
     X = np.random.default_rng(0).standard_normal((300, 8))
     X[17, 3] = np.inf
