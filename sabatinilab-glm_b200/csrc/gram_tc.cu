@@ -26,6 +26,8 @@
 #include <algorithm>
 #include <vector>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace sglm {
@@ -47,9 +49,11 @@ __device__ __forceinline__ double z_value(const double *X, long long ldx, const 
     return 1.0;
 }
 
+// One pass over Z = [X | Y | 1]: per column the largest magnitude (-> scale exponent E) and the lowest set
+// bit of any element (-> how many radix-128 digits represent the whole column exactly at that scale).
 __global__ void __launch_bounds__(256)
 tc_colmax_kernel(const double *__restrict__ X, long long ldx, const double *__restrict__ Y, long long ldy,
-                 int C, int n_y, long long T, unsigned long long *__restrict__ colmax_bits) {
+                 int C, int n_y, long long T, unsigned long long *__restrict__ colmax_bits, int *__restrict__ col_lsb) {
     const int n_aug = C + n_y + 1;
     const int c = blockIdx.x * 256 + threadIdx.x;
     if (c >= n_aug) return;
@@ -57,13 +61,20 @@ tc_colmax_kernel(const double *__restrict__ X, long long ldx, const double *__re
     const long long t0 = (long long)blockIdx.y * rows_per, t1 = min(T, t0 + rows_per);
     double m = 0.0;
     bool bad = false;
+    int lsb = 0x7fffffff;
     for (long long t = t0; t < t1; ++t) {
         const double v = fabs(z_value(X, ldx, Y, ldy, C, n_y, t, c));
         bad |= !(v <= 1.7976931348623157e308);          // NaN or inf
         m = fmax(m, v);
+        const long long bits = __double_as_longlong(v);
+        const int e = (int)(bits >> 52);
+        const long long frac = bits & 0xfffffffffffffLL;
+        if (e > 0) lsb = min(lsb, e - 1075 + __ffsll(frac | (1LL << 52)) - 1);       // v = (2^52 + frac) * 2^(e-1075)
+        else if (frac) lsb = min(lsb, -1074 + __ffsll(frac) - 1);                    // subnormal
     }
     if (bad) m = __longlong_as_double(0x7ff8000000000000LL);
     atomicMax(colmax_bits + c, (unsigned long long)__double_as_longlong(m));   // monotone for non-negative doubles; NaN pattern wins
+    atomicMin(col_lsb + c, lsb);
 }
 
 // number of radix digits (1..TC_SMAX) a value needs to be represented exactly at scale 2^E
@@ -97,14 +108,24 @@ tc_digits_kernel(const double *__restrict__ X, long long ldx, const double *__re
     atomicMax(colS + c, need);
 }
 
+// colS holds the column's lowest set bit on entry (0x7f7f7f7f.. when the column is all zero) and the number
+// of digit planes on exit: digit k carries the bits down to 2^(E - 6 - 7(k-1)), so the column is exact with
+// k >= (E - 6 - lsb) / 7 + 1 planes (the same count the digit-by-digit expansion of every element gives).
 __global__ void tc_exponent_kernel(const unsigned long long *__restrict__ colmax_bits, int n_aug,
                                    int *__restrict__ colE, int *__restrict__ colS, int *__restrict__ flag) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_aug) return;
     const double m = __longlong_as_double((long long)colmax_bits[c]);
     if (!(m <= 1.7976931348623157e308)) { atomicOr(flag, 1); colE[c] = 0; colS[c] = 1; return; }
-    colE[c] = (m == 0.0) ? 0 : ilogb(m) + 1;      // |z| < 2^E
-    colS[c] = 1;
+    const int E = (m == 0.0) ? 0 : ilogb(m) + 1;      // |z| < 2^E
+    colE[c] = E;
+    const int lsb = colS[c];
+    int need = 1;
+    if (m != 0.0) {
+        const int span = E - 6 - lsb;                 // bits below the first digit
+        if (span > 0) need = 1 + (span + 6) / 7;
+    }
+    colS[c] = min(need, TC_SMAX);
 }
 
 // ------------------------------------------------------------------ slicing (digits, transposed, gathered rows)
@@ -593,15 +614,17 @@ extern "C" int sglm_gram_tc_analyze_f64(const double *X, int64_t ldx, const doub
     const int n_aug = C + n_y + 1;
     SGLM_CUDA_OK(cudaMemsetAsync(colmax_scratch, 0, (size_t)n_aug * sizeof(uint64_t), st));
     SGLM_CUDA_OK(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    SGLM_CUDA_OK(cudaMemsetAsync(colS, 0x7f, (size_t)n_aug * sizeof(int), st));       // running minimum of the lowest set bit
     const int gy = (int)std::max<long long>(1, std::min<long long>(T / 256, 64LL * sm_count() / std::max(1, ceil_div(n_aug, 256))));
     dim3 grid(ceil_div(n_aug, 256), gy);
     if (T > 0) {
-        tc_colmax_kernel<<<grid, 256, 0, st>>>(X, ldx, Y, ldy, C, n_y, T, (unsigned long long *)colmax_scratch);
+        tc_colmax_kernel<<<grid, 256, 0, st>>>(X, ldx, Y, ldy, C, n_y, T, (unsigned long long *)colmax_scratch, colS);
         SGLM_LAUNCH_OK("tc_colmax_kernel");
     }
     tc_exponent_kernel<<<ceil_div(n_aug, 256), 256, 0, st>>>((const unsigned long long *)colmax_scratch, n_aug, colE, colS, flag);
     SGLM_LAUNCH_OK("tc_exponent_kernel");
-    if (T > 0) {
+    if (T > 0 && getenv("SGLM_TC_DIGIT_PASS")) {
+        // validation switch: the digit-by-digit second pass (atomicMax on colS) must not raise any count
         tc_digits_kernel<<<grid, 256, 0, st>>>(X, ldx, Y, ldy, C, n_y, T, colE, colS);
         SGLM_LAUNCH_OK("tc_digits_kernel");
     }
