@@ -181,7 +181,13 @@ def _gaussian_grid(Xd, yd, cv_idx, glms, rolls, score_method):
 
     if not bool(finite_flag.item()):
         raise ValueError("Input contains NaN, infinity or a value too large for dtype('float64').")
-    coef = Wd[:, :C].cpu().numpy()
+    n_sets_k = len(glms)
+    # coefficients leave the device already in the layout of the result dicts: [set][C][F] for the folds
+    # (cv_coefs is C x F, backend/sglm_cv.py:98) and [set][C] for the refits — one transposition on the
+    # device instead of one per parameter set on the host
+    W3 = Wd[:, :C].reshape(n_sets_k, F + 1, C)
+    coef_folds = W3[:, :F, :].permute(0, 2, 1).contiguous().cpu().numpy()      # [set][C][F]
+    coef_full = W3[:, F, :].contiguous().cpu().numpy()                          # [set][C]
     icpt = b_d.cpu().numpy()
     rss_test_h = rss_test.cpu().numpy()
     rss_train_h = rss_train.cpu().numpy()
@@ -193,46 +199,69 @@ def _gaussian_grid(Xd, yd, cv_idx, glms, rolls, score_method):
         yy = Gy[s, ycol, ycol]
         return n, sy, yy
 
-    results = []
-    for k, (glm, r) in enumerate(zip(glms, rolls)):
-        ycol = ycol_of_roll[r]
-        cv_coefs = np.zeros((C, F))
-        cv_intercepts = np.zeros(F)
-        s_tr, s_te = np.zeros(F), np.zeros(F)
-        rss_pool = tss_pool = n_pool = 0.0
-        base = k * (F + 1)
+    # per-fold moments of every y column (vectorised over the folds; the loop below runs once per set)
+    mom = {}
+    for ycol in sorted(set(ycol_of_roll.values())):
+        n_f = np.array([set_moments(1 + f, ycol)[0] for f in range(F)])
+        sy_f = np.array([set_moments(1 + f, ycol)[1] for f in range(F)])
+        yy_f = np.array([set_moments(1 + f, ycol)[2] for f in range(F)])
+        n_t, sy_t, yy_t = np.zeros(F), np.zeros(F), np.zeros(F)
+        n0, sy0, yy0 = set_moments(0, ycol)
         for f in range(F):
-            i = base + f
-            cv_coefs[:, f] = coef[i]
-            cv_intercepts[f] = icpt[i] if glm.model.fit_intercept else 0.0
-            n_f, sy_f, yy_f = set_moments(1 + f, ycol)
             if train_set[f] is None:
-                n0, sy0, yy0 = set_moments(0, ycol)
-                n_t, sy_t, yy_t = n0 - n_f, sy0 - sy_f, yy0 - yy_f
+                n_t[f], sy_t[f], yy_t[f] = n0 - n_f[f], sy0 - sy_f[f], yy0 - yy_f[f]
             else:
-                n_t, sy_t, yy_t = set_moments(train_set[f], ycol)
-            rte, rtr = max(rss_test_h[i], 0.0), max(rss_train_h[i], 0.0)
-            tss_f = yy_f - sy_f * sy_f / n_f if n_f > 0 else 0.0
-            tss_t = yy_t - sy_t * sy_t / n_t if n_t > 0 else 0.0
-            if score_method == 'r2':
-                s_tr[f] = _r2(rtr, tss_t)
-                s_te[f] = _r2(rte, tss_f)
-            else:
-                s_tr[f] = -rtr / n_t
-                s_te[f] = -rte / n_f
-            rss_pool += rte
-            tss_pool += max(tss_f, 0.0)
-            n_pool += n_f
+                n_t[f], sy_t[f], yy_t[f] = set_moments(train_set[f], ycol)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            tss_f = np.where(n_f > 0, yy_f - sy_f * sy_f / n_f, 0.0)
+            tss_t = np.where(n_t > 0, yy_t - sy_t * sy_t / n_t, 0.0)
+        mom[ycol] = (n_f, n_t, tss_f, tss_t)
+
+    def r2_vec(rss, tss):
+        with np.errstate(divide='ignore', invalid='ignore'):
+            return np.where(tss <= 0.0, np.where(rss == 0.0, 1.0, 0.0), 1.0 - rss / np.where(tss <= 0.0, 1.0, tss))
+
+    # scores of every (set, fold) at once
+    ycols = np.array([ycol_of_roll[r] for r in rolls], dtype=np.int64)
+    fi = np.array([bool(g.model.fit_intercept) for g in glms])
+    rte = np.maximum(rss_test_h.reshape(n_sets_k, F + 1)[:, :F], 0.0)
+    rtr = np.maximum(rss_train_h.reshape(n_sets_k, F + 1)[:, :F], 0.0)
+    icpt2 = icpt.reshape(n_sets_k, F + 1)
+    n_f = np.stack([mom[c][0] for c in ycols]) if n_sets_k else np.zeros((0, F))
+    n_t = np.stack([mom[c][1] for c in ycols]) if n_sets_k else np.zeros((0, F))
+    tss_f = np.stack([mom[c][2] for c in ycols]) if n_sets_k else np.zeros((0, F))
+    tss_t = np.stack([mom[c][3] for c in ycols]) if n_sets_k else np.zeros((0, F))
+    if score_method == 'r2':
+        S_tr, S_te = r2_vec(rtr, tss_t), r2_vec(rte, tss_f)
+    else:
+        with np.errstate(divide='ignore', invalid='ignore'):
+            S_tr, S_te = -rtr / n_t, -rte / n_f
+    rss_pool_a = np.zeros(n_sets_k)
+    tss_pool_a = np.zeros(n_sets_k)
+    n_pool_a = np.zeros(n_sets_k)
+    for f in range(F):                                   # left-to-right, as the reference accumulates fold by fold
+        rss_pool_a += rte[:, f]
+        tss_pool_a += np.maximum(tss_f[:, f], 0.0)
+        n_pool_a += n_f[:, f]
+    with np.errstate(divide='ignore', invalid='ignore'):
+        mean_tr = S_tr.mean(axis=1) if F else np.full(n_sets_k, np.nan)
+        mean_te = S_te.mean(axis=1) if F else np.full(n_sets_k, np.nan)
+        std_te = S_te.std(axis=1) if F else np.full(n_sets_k, np.nan)
+
+    results = []
+    for k, glm in enumerate(glms):
+        base = k * (F + 1)
+        rss_pool, tss_pool, n_pool = rss_pool_a[k], tss_pool_a[k], n_pool_a[k]
         i_full = base + F
-        _set_fitted(glm, coef[i_full], icpt[i_full], info[i_full], status[i_full])
+        _set_fitted(glm, coef_full[k], icpt[i_full], info[i_full], status[i_full])
         results.append({
-            'cv_coefs': cv_coefs,
-            'cv_intercepts': cv_intercepts,
-            'cv_scores_train': s_tr,
-            'cv_scores_test': s_te,
-            'cv_mean_score_train': np.mean(s_tr),
-            'cv_mean_score': np.mean(s_te),
-            'cv_std_score': np.std(s_te),
+            'cv_coefs': coef_folds[k],
+            'cv_intercepts': icpt2[k, :F].copy() if fi[k] else np.zeros(F),
+            'cv_scores_train': S_tr[k].copy(),
+            'cv_scores_test': S_te[k].copy(),
+            'cv_mean_score_train': mean_tr[k],
+            'cv_mean_score': mean_te[k],
+            'cv_std_score': std_te[k],
             'cv_R2_score': 0 if tss_pool == 0 else 1 - rss_pool / tss_pool,      # sglm.calc_R2
             'cv_mse_score': rss_pool / n_pool if n_pool else np.nan,
             'model': glm,
