@@ -219,6 +219,10 @@ int sglm_finalize_models_f64(const double *W, int64_t ldw, int32_t C, int32_t n_
 /* (a11) scores from statistics: out[m] = V[m]' A V[m]  (A symmetric n x n). */
 int sglm_quadform_f64(const double *A, int64_t lda, int32_t n, const double *V, int64_t ldv,
                       int32_t n_models, double *out, void *stream);
+/* Row-split form for few models: partial[s * n_models + m] = sum over the rows of split s of v_m[i] (A v_m)[i];
+ * the caller adds the n_splits partial sums in order. */
+int sglm_quadform_split_f64(const double *A, int64_t lda, int32_t n, const double *V, int64_t ldv,
+                            int32_t n_models, int32_t n_splits, double *partial, void *stream);
 
 /* ------------------------------------------------------------------------- *
  * (a10, a11) explicit-matrix paths: GLM.predict / neg_mse_score / r2_score /

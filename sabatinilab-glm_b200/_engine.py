@@ -588,11 +588,19 @@ def finalize(W, C, n_y, models):
 def quadform(A, V):
     """out[m] = V[m]' A V[m]."""
     M = V.shape[0]
-    out = _empty((M,))
     n = A.shape[0]
-    if M:
+    if not M:
+        return _empty((0,))
+    # few models: split the rows of A over several CTAs per model group so that every SM streams a part
+    groups = (M + 7) // 8
+    splits = max(1, min(16, (2 * 148) // groups))
+    if splits == 1:
+        out = _empty((M,))
         call("sglm_quadform_f64", ptr(A), A.stride(0), n, ptr(V), V.stride(0), M, ptr(out), stream_ptr())
-    return out
+        return out
+    part = _empty((splits, M))
+    call("sglm_quadform_split_f64", ptr(A), A.stride(0), n, ptr(V), V.stride(0), M, splits, ptr(part), stream_ptr())
+    return part.sum(dim=0)
 
 
 # --------------------------------------------------------------------------- #

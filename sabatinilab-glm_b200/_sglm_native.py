@@ -51,6 +51,7 @@ _PROTOTYPES = {
     "sglm_finalize_models_f64": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp,
                                          c_vp, c_i64, c_vp]),
     "sglm_quadform_f64": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_vp, c_vp]),
+    "sglm_quadform_split_f64": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
     "sglm_predict_f64": (c_i32, [c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp]),
     "sglm_score_workspace_bytes": (c_sz, []),
     "sglm_score_f64": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp,

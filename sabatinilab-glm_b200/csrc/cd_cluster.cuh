@@ -101,7 +101,7 @@ __device__ __forceinline__ void st_async_b64(unsigned ra, unsigned long long v, 
 }
 __device__ __forceinline__ bool mbar_try_wait(unsigned a, unsigned parity) {
     unsigned ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(a), "r"(parity) : "memory");
     return ok != 0;
 }

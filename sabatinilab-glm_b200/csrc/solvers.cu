@@ -627,7 +627,8 @@ quadform_kernel(const double *__restrict__ A, long long lda, int n, const double
     double acc[QF_MB];
 #pragma unroll
     for (int mm = 0; mm < QF_MB; ++mm) acc[mm] = 0.0;
-    for (int i = warp; i < n; i += QF_THREADS / 32) {
+    // rows i = warp + 8 * (blockIdx.y + k * gridDim.y): the row splits of gridDim.y > 1 write partial sums
+    for (int i = warp + (QF_THREADS / 32) * blockIdx.y; i < n; i += (QF_THREADS / 32) * gridDim.y) {
         const double *row = A + (long long)i * lda;
         double d[QF_MB];
 #pragma unroll
@@ -637,12 +638,13 @@ quadform_kernel(const double *__restrict__ A, long long lda, int n, const double
 #pragma unroll
             for (int mm = 0; mm < QF_MB; ++mm) d[mm] += aij * vs[mm * n + j];
         }
+        // v' A v is linear in the lane partials of row i, so they are weighted by v_i here and reduced over
+        // the warp once at the end (a shuffle reduction per row and model was most of this kernel's time)
 #pragma unroll
-        for (int mm = 0; mm < QF_MB; ++mm) {
-            d[mm] = warp_sum(d[mm]);
-            acc[mm] += d[mm] * vs[mm * n + i];
-        }
+        for (int mm = 0; mm < QF_MB; ++mm) acc[mm] += d[mm] * vs[mm * n + i];
     }
+#pragma unroll
+    for (int mm = 0; mm < QF_MB; ++mm) acc[mm] = warp_sum(acc[mm]);
     __shared__ double red[QF_THREADS / 32][QF_MB];
     if (lane == 0)
         for (int mm = 0; mm < QF_MB; ++mm) red[warp][mm] = acc[mm];
@@ -650,7 +652,7 @@ quadform_kernel(const double *__restrict__ A, long long lda, int n, const double
     if (tid < nm) {
         double s = 0.0;
         for (int w = 0; w < QF_THREADS / 32; ++w) s += red[w][tid];
-        out[m0 + tid] = s;
+        out[(long long)blockIdx.y * n_models + m0 + tid] = s;
     }
 }
 
@@ -762,8 +764,24 @@ extern "C" int sglm_finalize_models_f64(const double *W, int64_t ldw, int32_t C,
     return SGLM_OK;
 }
 
+static int quadform_launch(const double *A, int64_t lda, int32_t n, const double *V, int64_t ldv, int32_t n_models,
+                           int32_t n_splits, double *out, void *stream);
+
 extern "C" int sglm_quadform_f64(const double *A, int64_t lda, int32_t n, const double *V, int64_t ldv,
                                  int32_t n_models, double *out, void *stream) {
+    return quadform_launch(A, lda, n, V, ldv, n_models, 1, out, stream);
+}
+
+// Row-split form: partial[s * n_models + m] = sum over the rows of split s of v_m[i] (A v_m)[i]; the caller adds
+// the n_splits partial sums (fixed order: deterministic).  Few models (a fold's 250) otherwise leave most SMs idle.
+extern "C" int sglm_quadform_split_f64(const double *A, int64_t lda, int32_t n, const double *V, int64_t ldv,
+                                       int32_t n_models, int32_t n_splits, double *partial, void *stream) {
+    SGLM_CHECK_ARG(n_splits >= 1 && n_splits <= 65535, SGLM_E_INVALID_ARG, "quadform_split: bad n_splits");
+    return quadform_launch(A, lda, n, V, ldv, n_models, n_splits, partial, stream);
+}
+
+static int quadform_launch(const double *A, int64_t lda, int32_t n, const double *V, int64_t ldv, int32_t n_models,
+                           int32_t n_splits, double *out, void *stream) {
     SGLM_CHECK_ARG(n > 0 && n_models >= 0 && lda >= n && ldv >= n, SGLM_E_SHAPE, "quadform: bad shape");
     if (n_models == 0) return SGLM_OK;
     SGLM_CHECK_ARG(A && V && out, SGLM_E_INVALID_ARG, "quadform: null pointer");
@@ -772,10 +790,10 @@ extern "C" int sglm_quadform_f64(const double *A, int64_t lda, int32_t n, const 
     SGLM_CHECK_ARG(smem <= 227 * 1024, SGLM_E_UNSUPPORTED, "quadform: n=%d too large for shared memory", n);
     if (mb == 8) {
         SGLM_CUDA_OK(cudaFuncSetAttribute(quadform_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        quadform_kernel<8><<<ceil_div(n_models, 8), QF_THREADS, smem, (cudaStream_t)stream>>>(A, lda, n, V, ldv, n_models, out);
+        quadform_kernel<8><<<dim3(ceil_div(n_models, 8), n_splits), QF_THREADS, smem, (cudaStream_t)stream>>>(A, lda, n, V, ldv, n_models, out);
     } else {
         SGLM_CUDA_OK(cudaFuncSetAttribute(quadform_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        quadform_kernel<4><<<ceil_div(n_models, 4), QF_THREADS, smem, (cudaStream_t)stream>>>(A, lda, n, V, ldv, n_models, out);
+        quadform_kernel<4><<<dim3(ceil_div(n_models, 4), n_splits), QF_THREADS, smem, (cudaStream_t)stream>>>(A, lda, n, V, ldv, n_models, out);
     }
     SGLM_LAUNCH_OK("quadform_kernel");
     return SGLM_OK;
