@@ -142,17 +142,22 @@ tc_slice_kernel(const double *__restrict__ X, long long ldx, const double *__res
     const long long p0 = (long long)blockIdx.x * 128;
     const int c0 = blockIdx.y * 32;
     const int tid = threadIdx.x;
+    // the 128 row indices first (one coalesced load), so that the 16 element loads of a thread below do not
+    // each wait for their own index: 16 independent loads in flight per thread
+    __shared__ long long srow[128];
+    if (tid < 128) srow[tid] = (p0 + tid < n_pos) ? rows[p0 + tid] : -1;
+    __syncthreads();
     // load 128 positions x 32 columns, coalesced along the columns of the row-major source
-    for (int i = tid; i < 128 * 32; i += 256) {
-        const int r = i >> 5, cc = i & 31;
-        const long long p = p0 + r;
-        const int c = c0 + cc;
-        double v = 0.0;
-        if (p < n_pos && c < n_aug) {
-            const long long t = rows[p];
-            if (t >= 0) v = z_value(X, ldx, Y, ldy, C, n_y, t, c);
+    {
+        const int cc = tid & 31, c = c0 + cc;
+        double v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const long long t = srow[(tid >> 5) + 8 * k];
+            v[k] = (t >= 0 && c < n_aug) ? z_value(X, ldx, Y, ldy, C, n_y, t, c) : 0.0;
         }
-        tile[cc][r] = v;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) tile[cc][(tid >> 5) + 8 * k] = v[k];
     }
     __syncthreads();
     // thread <-> (4 consecutive positions, 4 columns): one packed 32-bit store per digit plane,
@@ -434,15 +439,25 @@ tc_gram_i8_check_kernel(const int8_t *__restrict__ At, long long ld_at, const in
 // SGout[o][e] = sum over the cells c with member[o * n_cells + c] != 0 of SG[c][e]: the row sets of a CV grid
 // overlap (the full data contain every test fold, random folds intersect), so the GEMM runs once over the
 // disjoint CELLS of the partition they induce and the Gram of each set is the sum of its cells' Grams.
+constexpr int TC_SUM_OUT = 8;      // output sets accumulated per pass over the cells
 __global__ void __launch_bounds__(256)
 tc_cell_sum_kernel(const long long *__restrict__ SG, long long n_elem, int n_cells, const int *__restrict__ member,
                    int n_out, long long *__restrict__ SGout) {
+    // every cell element is read once per group of TC_SUM_OUT output sets and added to the sets it belongs to
     for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < n_elem; e += (long long)gridDim.x * 256) {
-        for (int o = 0; o < n_out; ++o) {
-            long long acc = 0;
-            for (int c = 0; c < n_cells; ++c)
-                if (member[o * n_cells + c]) acc += SG[(long long)c * n_elem + e];
-            SGout[(long long)o * n_elem + e] = acc;
+        for (int o0 = 0; o0 < n_out; o0 += TC_SUM_OUT) {
+            long long acc[TC_SUM_OUT];
+#pragma unroll
+            for (int k = 0; k < TC_SUM_OUT; ++k) acc[k] = 0;
+            for (int c = 0; c < n_cells; ++c) {
+                const long long v = SG[(long long)c * n_elem + e];
+#pragma unroll
+                for (int k = 0; k < TC_SUM_OUT; ++k)
+                    if (o0 + k < n_out && member[(o0 + k) * n_cells + c]) acc[k] += v;
+            }
+#pragma unroll
+            for (int k = 0; k < TC_SUM_OUT; ++k)
+                if (o0 + k < n_out) SGout[(long long)(o0 + k) * n_elem + e] = acc[k];
         }
     }
 }
