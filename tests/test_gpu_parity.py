@@ -576,6 +576,35 @@ def test_config2_ridge_cv_grid_vs_oracle():
             assert coef_rel_err(a["model"].coef_, b["model"].coef_) < 1e-7
 
 
+def test_config3_elasticnet_cv_grid_vs_oracle():
+    """configs[2] shape (50 shifts, > 1024 columns, random overlapping folds) at reduced T: the whole wide-design
+    path — Gram over the disjoint cells of the row sets, coordinate descent as cluster + per-model launch plan,
+    row-split quadratic forms — against the oracle's CV grid (scikit-learn fits)."""
+    import synth_data
+    X0, shifts, Xd, y = _session(5_000, 24, 20, 29, 303)
+    assert Xd.shape[1] == 1200 and len(shifts) == 50
+    cv_idx = synth_data.synth_folds(Xd.shape[0], 3, 303, group=250)
+    grid = [dict(alpha=float(a), l1_ratio=float(l), max_iter=1000, fit_intercept=True, tol=1e-4)
+            for l in (0.2, 0.9) for a in np.logspace(-2.5, -0.5, 3)]
+    want = orc.cv_glm_mult_params(Xd, y, cv_idx, "Gaussian", [dict(g) for g in grid], score_method="r2",
+                                  engine="sklearn")
+    got = sglm_cv.cv_glm_mult_params(Xd, y, cv_idx, "Gaussian", [dict(g) for g in grid], score_method="r2")
+    assert nat.last_tc_plan["cells"]                                       # overlapping folds went through the cells
+    assert eng._cd_plan(1200, len(grid) * 4)[0][2:] == (4, 2)              # ... and the heavy models through clusters
+    assert got["best_params"] == want["best_params"]
+    assert abs(got["best_score"] - want["best_score"]) < 1e-6
+    for a, b in zip(got["full_cv_results"], want["full_cv_results"]):
+        for k in range(3):
+            assert coef_rel_err(a["cv_coefs"][:, k], b["cv_coefs"][:, k]) < 1e-4
+        assert np.allclose(a["cv_intercepts"], b["cv_intercepts"], atol=1e-8)
+        assert np.allclose(a["cv_scores_test"], b["cv_scores_test"], atol=1e-6)
+        assert np.allclose(a["cv_scores_train"], b["cv_scores_train"], atol=1e-6)
+        assert abs(a["cv_R2_score"] - b["cv_R2_score"]) < 1e-6
+        assert abs(a["cv_mse_score"] - b["cv_mse_score"]) < 1e-6
+        assert coef_rel_err(a["model"].coef_, b["model"].coef_) < 1e-4
+        assert a["model"].model.n_iter_ == b["model"].model.n_iter_
+
+
 def test_config4_poisson_alpha_sweep_vs_sklearn_optimum():
     """configs[3] shape (20 predictors x 40 shifts) at reduced T, against TweedieRegressor driven
     to its optimum (newton-cholesky, tol 1e-12)."""
