@@ -186,6 +186,8 @@ int sglm_enet_cd_gram_f64(const double *const *prob_Q, const double *const *prob
  * sglm_enet_cd_cluster_supported(group_size, cluster_size) -> 1 if that shape is compiled in. */
 int sglm_enet_cd_cluster_supported(int32_t group_size, int32_t cluster_size);
 size_t sglm_enet_cd_cluster_tmap_bytes(void);
+/* shared memory per CTA of that shape for C columns (must stay <= 227 KB; 0 = shape not compiled in) */
+size_t sglm_enet_cd_cluster_smem_bytes(int32_t group_size, int32_t cluster_size, int32_t C);
 int sglm_enet_cd_cluster_encode_tmaps(const uint64_t *Q_dev_ptrs, int32_t n_prob, int32_t C, int64_t ldq, void *out);
 int sglm_enet_cd_cluster_f64(const double *const *prob_Q, const double *const *prob_q,
                              const double *const *prob_diag, const double *prob_yy, int64_t ldq, int32_t C,

@@ -356,6 +356,16 @@ def _cd_shape_ok(g, k, C):
         k //= 2
     if not nat.lib().sglm_enet_cd_cluster_supported(g, k):
         raise nat.SglmNativeError(f"coordinate descent: unsupported (group, cluster) = ({g}, {k})")
+    # very wide designs: a CTA's column slice (w and Qw of every model of the group) must fit in shared memory
+    # — widen the cluster, then shrink the group, else fall back to one CTA per model
+    limit = 227 * 1024
+    while nat.lib().sglm_enet_cd_cluster_smem_bytes(g, k, C) > limit:
+        if k < 8 and (C + 31) // 32 >= 4 * k:
+            k *= 2
+        elif g > 1:
+            g //= 2
+        else:
+            return 0, 0
     return g, k
 
 

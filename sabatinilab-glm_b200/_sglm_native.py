@@ -44,6 +44,7 @@ _PROTOTYPES = {
     "sglm_enet_cd_cluster_f64": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                                          c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "sglm_enet_cd_cluster_tmap_bytes": (c_sz, []),
+    "sglm_enet_cd_cluster_smem_bytes": (c_sz, [c_i32, c_i32, c_i32]),
     "sglm_enet_cd_cluster_encode_tmaps": (c_i32, [c_vp, c_i32, c_i32, c_i64, c_vp]),
     "sglm_ridge_workspace_bytes": (c_sz, [c_i32, c_i64, c_i32]),
     "sglm_ridge_solve_f64": (c_i32, [c_vp, c_i64, c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp, c_vp,

@@ -51,6 +51,14 @@ extern "C" int sglm_enet_cd_cluster_encode_tmaps(const uint64_t *Q_dev_ptrs, int
     return SGLM_OK;
 }
 
+// Shared memory one CTA of the (group_size, cluster_size) shape needs for a design of C columns (0 = shape not
+// compiled in): the host picks a larger cluster (narrower column slice per CTA) or the per-model kernel when
+// this exceeds the 227 KB a CTA can have.
+extern "C" size_t sglm_enet_cd_cluster_smem_bytes(int32_t group_size, int32_t cluster_size, int32_t C) {
+    if (!sglm_enet_cd_cluster_supported(group_size, cluster_size) || C <= 0) return 0;
+    return cdc::make_layout(group_size, cluster_size, 8, C).total;
+}
+
 extern "C" int sglm_enet_cd_cluster_f64(const double *const *prob_Q, const double *const *prob_q,
                                         const double *const *prob_diag, const double *prob_yy, int64_t ldq,
                                         int32_t C, const int32_t *prob_of_group, const int32_t *model_of_slot,

@@ -166,6 +166,9 @@ def test_cd_launch_plan_parsing():
         eng.CD_PLAN = None
         assert eng._cd_plan(410, 1500) == [(0, 1500, 0, 0)]       # narrow design: one CTA per model
         assert eng._cd_plan(2000, 1500)[0][2:] == (4, 2)
+        eng.CD_PLAN = "4x2"
+        assert eng._cd_plan(6000, 100) == [(0, 100, 4, 4)]       # slice of 3000 columns x 4 models does not fit: wider cluster
+        assert eng._cd_plan(20000, 100)[0][2] in (1, 2)          # ... then smaller groups
         eng.CD_PLAN = "3x2"
         with pytest.raises(Exception):
             eng._cd_plan(2000, 10)
