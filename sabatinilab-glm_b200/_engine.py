@@ -545,16 +545,35 @@ def solve_models(models, C, do_screening=True):
     for i, m in enumerate(models):
         if m.kind in ("ridge", "ols"):
             groups.setdefault(id(m.problem), []).append(i)
-    for idxs in groups.values():
+    # one Cholesky launch per problem (one CTA per alpha): the launches of the problems of a grid are independent
+    # and each fills only a few SMs, so they go to separate streams and run side by side
+    launched = []
+    if groups:
+        main = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(main)
+    for gi, idxs in enumerate(groups.values()):
         p = models[idxs[0]].problem
-        alphas = _dev([0.0 if models[i].kind == "ols" else models[i].alpha for i in idxs], np.float64)
         n_a = len(idxs)
         wb = nat.lib().sglm_ridge_workspace_bytes(C, p.ldq, n_a)
-        work = torch.empty(wb // 8, dtype=torch.float64, device="cuda")
-        Wr = _empty((n_a, ldw))
-        st = torch.empty(n_a, dtype=torch.int32, device="cuda")
-        call("sglm_ridge_solve_f64", ptr(p.Qc), p.ldq, ptr(p.qc), C, ptr(alphas), n_a, ptr(Wr), ldw, ptr(st),
-             ptr(work), wb, stream_ptr())
+        st_ = main if gi == 0 else _side_stream(100 + gi % 8)
+        if st_ is not main:
+            st_.wait_event(ready)
+        with torch.cuda.stream(st_):
+            alphas = _dev([0.0 if models[i].kind == "ols" else models[i].alpha for i in idxs], np.float64)
+            work = torch.empty(wb // 8, dtype=torch.float64, device="cuda")
+            Wr = _empty((n_a, ldw))
+            st = torch.empty(n_a, dtype=torch.int32, device="cuda")
+            call("sglm_ridge_solve_f64", ptr(p.Qc), p.ldq, ptr(p.qc), C, ptr(alphas), n_a, ptr(Wr), ldw, ptr(st),
+                 ptr(work), wb, stream_ptr())
+            if st_ is not main:
+                ev = torch.cuda.Event()
+                ev.record(st_)
+                main.wait_event(ev)
+                for t in (alphas, work, Wr, st):
+                    t.record_stream(st_)
+        launched.append((idxs, p, Wr, st, work, alphas))
+    for idxs, p, Wr, st, work, alphas in launched:
         st_h = st.cpu().numpy()
         for k, i in enumerate(idxs):
             if st_h[k] != 0 and models[i].kind == "ols":
@@ -569,7 +588,7 @@ def solve_models(models, C, do_screening=True):
                 st_h[k] = 0
         W.index_copy_(0, _dev(idxs, np.int64), Wr)
         status[idxs] = st_h * 2                                        # 2 = not positive definite
-        del work
+    del launched
     return W, info, status
 
 
