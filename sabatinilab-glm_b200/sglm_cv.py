@@ -301,6 +301,10 @@ def _poisson_grid(Xd, yd, cv_idx, glms, rolls, score_method):
     _, te_w, _, n_te, _ = _fold_weights(cv_idx, T)
     tr_w = [eng.index_counts(train, T) for (train, _) in cv_idx]
     results = []
+    # Every IRLS run is driven to the optimum (Newton step below 1e-8), so the starting point only changes the
+    # number of iterations: the refit starts from the previous parameter set's refit, the folds from the refit
+    # of their own parameter set (a few Newton steps instead of a cold start from log(mean y)).
+    prev_full = None
     for glm, r in zip(glms, rolls):
         est = glm.model
         est._check_family()
@@ -309,8 +313,13 @@ def _poisson_grid(Xd, yd, cv_idx, glms, rolls, score_method):
         cv_intercepts = np.zeros(F)
         s_tr, s_te = np.zeros(F), np.zeros(F)
         rss_pool = tss_pool = n_pool = 0.0
+        init = prev_full if (prev_full is not None and prev_full[2] == bool(est.fit_intercept)) else (None, None, None)
+        w_full, b_full, n_it_full = eng.poisson_irls(Xd, yd, est.alpha, est.fit_intercept, None, est.max_iter, est.tol,
+                                                     coef_init=init[0], intercept_init=init[1])
+        prev_full = (w_full, b_full, bool(est.fit_intercept))
         for f in range(F):
-            w, b, _ = eng.poisson_irls(Xd, y_r, est.alpha, est.fit_intercept, tr_w[f], est.max_iter, est.tol)
+            w, b, _ = eng.poisson_irls(Xd, y_r, est.alpha, est.fit_intercept, tr_w[f], est.max_iter, est.tol,
+                                       coef_init=w_full if not r else None, intercept_init=b_full if not r else None)
             cv_coefs[:, f], cv_intercepts[f] = w, b
             st, _ = eng.score_sums(Xd, y_r, w, b, 1, rw=tr_w[f])
             se, _ = eng.score_sums(Xd, y_r, w, b, 1, rw=te_w[f])
@@ -321,7 +330,7 @@ def _poisson_grid(Xd, yd, cv_idx, glms, rolls, score_method):
             rss_pool += se[1]
             tss_pool += se[3] - se[2] * se[2] / se[0]
             n_pool += se[0]
-        w, b, n_it = eng.poisson_irls(Xd, yd, est.alpha, est.fit_intercept, None, est.max_iter, est.tol)
+        w, b, n_it = w_full, b_full, n_it_full
         est.coef_, est.intercept_, est.n_iter_ = w, b, n_it
         glm.coef_ = glm.beta_ = w
         glm.intercept_ = glm.beta0_ = b
