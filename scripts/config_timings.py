@@ -13,6 +13,7 @@ def session(T, P, lo, hi, seed, poisson=False):
     def design():
         return sglm_pp.timeshift_multiple(X0, shift_amt_list=shifts)[h_lo:T - h_hi]
     X = design()
+    torch.manual_seed(seed)           # reproducible noise: the selected alpha is part of the record
     s = X @ beta
     if poisson:
         z = (s - s.mean()) / s.std()
