@@ -120,6 +120,24 @@ int sglm_gram_tc_f64(const double *X, int64_t ldx, const double *Y, int64_t ldy,
                      int64_t ldg, void *workspace, size_t workspace_bytes, int32_t use_check_gemm,
                      void *stream);
 
+/* Weighted tensor-core Gram: rows of Z scaled by row_scale[t] (sqrt of a row weight: G = Z' diag(w) Z) and at
+ * most max_planes digit planes per column (fewer than a column needs = digits rounded at the last plane,
+ * relative error 2^-(7 max_planes)).  Replaces the X'WX of every Newton / IRLS step of the Poisson fit
+ * (sklearn _glm/_newton_solver.py:315-359) as an APPROXIMATE Hessian; the gradient stays exact (sglm_xt_vec_f64). */
+int sglm_gram_tc_analyze_scaled_f64(const double *X, int64_t ldx, const double *Y, int64_t ldy, int32_t n_y,
+                                    int64_t T, int32_t C, const double *row_scale, int32_t max_planes,
+                                    int32_t *colE, int32_t *colS, uint64_t *colmax_scratch, int32_t *flag,
+                                    void *stream);
+int sglm_gram_tc_scaled_f64(const double *X, int64_t ldx, const double *Y, int64_t ldy, int32_t n_y, int64_t T,
+                            int32_t C, const double *row_scale, const int32_t *colE, const int32_t *colS,
+                            const int32_t *colS_host, int32_t n_sets, const int64_t *set_rows_host,
+                            const int64_t *rows, double *G, int64_t ldg, void *workspace,
+                            size_t workspace_bytes, void *stream);
+/* out[c] = sum_t X[t][c] r[t] (X'r: the exact gradient of a GLM loss), one pass over X, deterministic. */
+size_t sglm_xt_vec_workspace_bytes(int32_t C);
+int sglm_xt_vec_f64(const double *X, int64_t ldx, const double *r, int64_t T, int32_t C, double *out,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
 /* The same statistics from DISJOINT cells.  The row sets of a CV grid overlap (the full data contain every
  * test fold, random folds intersect); the partition they induce has n_cells cells, the int8 GEMM runs once over
  * every row (not once per set), and the Gram of output set o is the exact integer sum of the cells with
@@ -209,6 +227,10 @@ size_t sglm_ridge_workspace_bytes(int32_t C, int64_t ldq, int32_t n_alpha);
 int sglm_ridge_solve_f64(const double *Qc, int64_t ldq, const double *qc, int32_t C,
                          const double *alpha, int32_t n_alpha, double *W, int64_t ldw,
                          int32_t *status, void *work, size_t work_bytes, void *stream);
+/* x = (L L')^-1 rhs with the Cholesky factor of system k that sglm_ridge_solve_f64 left in `work`
+ * (a solve without a second factorisation: chord iterations of the Poisson Newton solver). */
+int sglm_chol_solve_f64(const void *work, int64_t ldq, int32_t C, int32_t k, const double *rhs, double *out,
+                        void *stream);
 
 /* Intercepts and augmented evaluation vectors (sklearn _set_intercept,
  * _coordinate_descent.py:1281):  b[m] = ybar[p] - xbar[p].w_m  (0 if xbar NULL)

@@ -686,6 +686,55 @@ def poisson_d2_from_sums(s):
 # --------------------------------------------------------------------------- #
 # (a9) Poisson by IRLS (Newton) — weighted statistics on the tensor path, Cholesky step
 # --------------------------------------------------------------------------- #
+POISSON_TC_PLANES = 4        # digit planes of the approximate Newton Hessian (4 x 7 bits)
+POISSON_TC = None            # None: large problems; False: always the exact fp64 DMMA Gram (IRLS form)
+
+
+def _poisson_tc(T, C):
+    import os
+    mode = os.environ.get("SGLM_POISSON_TC", "auto") if POISSON_TC is None else ("1" if POISSON_TC else "0")
+    if mode in ("0", "1"):
+        return mode == "1"
+    return T * C * C >= (1 << 36)
+
+
+def suffstats_tc_scaled(Xd, Yd, rs, max_planes, rows=None):
+    """G = Z' diag(rs^2) Z, Z = [X | Y | 1], from at most `max_planes` digit planes per column (approximate when a
+    column needs more): the weighted Gram of a Newton step on the tcgen05 path.  Returns G [1, n_aug, ldg]."""
+    torch = nat.require_cuda()
+    T, C = Xd.shape
+    n_y = Yd.shape[1]
+    n_aug = C + n_y + 1
+    ldg = _round_up(n_aug, 8)
+    colE = torch.empty(n_aug, dtype=torch.int32, device="cuda")
+    colS = torch.empty(n_aug, dtype=torch.int32, device="cuda")
+    scratch = torch.empty(n_aug, dtype=torch.int64, device="cuda")
+    flag = torch.empty(1, dtype=torch.int32, device="cuda")
+    call("sglm_gram_tc_analyze_scaled_f64", ptr(Xd), row_stride(Xd), ptr(Yd), row_stride(Yd), n_y, T, C, ptr(rs),
+         int(max_planes), ptr(colE), ptr(colS), ptr(scratch), ptr(flag), stream_ptr())
+    host = torch.cat([colS, flag]).cpu().numpy()
+    if host[-1] != 0:
+        raise ValueError("Input contains NaN, infinity or a value too large for dtype('float64').")
+    colS_h = np.ascontiguousarray(host[:-1], dtype=np.int32)
+    if rows is None:
+        rows = torch.arange(T, dtype=torch.int64, device="cuda")
+    pad = (-T) % 128
+    if pad:
+        rows = torch.cat([rows, torch.full((pad,), -1, dtype=torch.int64, device="cuda")])
+    sizes = np.ascontiguousarray([T], dtype=np.int64)
+    colS_p, sizes_p = colS_h.ctypes.data_as(ctypes.c_void_p), sizes.ctypes.data_as(ctypes.c_void_p)
+    ws_bytes = nat.lib().sglm_gram_tc_workspace_bytes(n_aug, colS_p, 1, sizes_p)
+    if ws_bytes == 0:
+        raise nat.SglmNativeError("gram_tc: invalid plan")
+    raw = torch.empty(ws_bytes + 1024, dtype=torch.uint8, device="cuda")
+    off = (-raw.data_ptr()) % 1024
+    G = _zeros((1, n_aug, ldg))
+    call("sglm_gram_tc_scaled_f64", ptr(Xd), row_stride(Xd), ptr(Yd), row_stride(Yd), n_y, T, C, ptr(rs), ptr(colE),
+         ptr(colS), colS_p, 1, sizes_p, ptr(rows), ptr(G), ldg, ctypes.c_void_p(raw.data_ptr() + off), ws_bytes,
+         stream_ptr())
+    return G
+
+
 def poisson_irls(Xd, yd, alpha, fit_intercept=True, rw=None, max_iter=100, tol=1e-4, coef_init=None,
                  intercept_init=None):
     """argmin mean(mu - y*eta) + alpha/2 |w|^2 (rows weighted by multiplicity rw).
@@ -724,6 +773,12 @@ def poisson_irls(Xd, yd, alpha, fit_intercept=True, rw=None, max_iter=100, tol=1
     wb = nat.lib().sglm_ridge_workspace_bytes(C, _round_up(C, 8), 1)
     work = torch.empty(wb // 8, dtype=torch.float64, device="cuda")
     st = torch.empty(1, dtype=torch.int32, device="cuda")
+    use_tc = _poisson_tc(T, C)
+    refresh, last_step, hess, h11 = True, np.inf, None, None
+    if use_tc:
+        tc_rows = torch.arange(T, dtype=torch.int64, device="cuda")
+        g_w = _empty((C,))
+        xt_ws = torch.empty(nat.lib().sglm_xt_vec_workspace_bytes(C) // 8, dtype=torch.float64, device="cuda")
     while True:
         call("sglm_poisson_irls_prepare_f64", ptr(Xd), row_stride(Xd), ptr(yd), ptr(rw), T, C, ptr(w), ptr(b),
              ptr(weight), ptr(z), ptr(sums), ptr(ws), stream_ptr())
@@ -732,25 +787,66 @@ def poisson_irls(Xd, yd, alpha, fit_intercept=True, rw=None, max_iter=100, tol=1
             w = 0.5 * (w + w_prev)
             b = 0.5 * (b + b_prev)
             halvings += 1
+            refresh = True
             continue
         halvings = 0
         if n_iter >= max_iter:
             break
-        G = suffstats(Xd, z, weight, rows_hint)
-        p = center(G[0], None, C, 1, 0, fit_intercept)
-        w_new = _zeros((1, ldw))
-        call("sglm_ridge_solve_f64", ptr(p.Qc), p.ldq, ptr(p.qc), C, ptr(alphas), 1, ptr(w_new), ldw, ptr(st),
-             ptr(work), wb, stream_ptr())
-        fetch_scalars([p])
-        b_new = _zeros((1,))
-        if fit_intercept:
-            b_new[0] = p.ybar - float((p.xbar * w_new[0, :C]).sum().item())
+        if use_tc:
+            # Newton step with an APPROXIMATE Hessian and the EXACT gradient: X'WX (with the weighted column sums
+            # for the intercept) comes from the tcgen05 digit-plane Gram of sqrt(W) [X | z | 1] truncated to
+            # POISSON_TC_PLANES planes (relative error 2^-28), the gradient X'(mu - y) from one fp64 pass over X.
+            # (H~ + a n I) w_new = H~ w - g  has the same fixed point as the exact iteration (g + a n w = 0).
+            # The factorised Hessian is kept while the steps keep shrinking fast (chord iterations: one pass
+            # over X for the gradient and two triangular solves per step) and rebuilt when they do not.
+            r = weight[0] - (yd if rw is None else rw * yd)                    # rw * (mu - y)
+            call("sglm_xt_vec_f64", ptr(Xd), row_stride(Xd), ptr(r), T, C, ptr(g_w), ptr(xt_ws), xt_ws.numel() * 8,
+                 stream_ptr())
+            g_b = sums[1] - sums[3]
+            w_new = _zeros((1, ldw))
+            if refresh:
+                rs = weight[0].sqrt()
+                G = suffstats_tc_scaled(Xd, z, rs, POISSON_TC_PLANES, tc_rows)
+                hess = center(G[0], None, C, 1, 0, fit_intercept)
+                h11 = sums[1].clone()
+                del G, rs
+            rhs = hess.Qc[:, :C] @ w[:C] - g_w
+            if fit_intercept:
+                rhs = rhs + hess.xbar * g_b
+            if refresh:
+                hess.qc.copy_(rhs)
+                call("sglm_ridge_solve_f64", ptr(hess.Qc), hess.ldq, ptr(hess.qc), C, ptr(alphas), 1, ptr(w_new), ldw,
+                     ptr(st), ptr(work), wb, stream_ptr())
+            else:
+                call("sglm_chol_solve_f64", ptr(work), hess.ldq, C, 0, ptr(rhs.contiguous()), ptr(w_new), stream_ptr())
+            b_new = _zeros((1,))
+            if fit_intercept:
+                b_new = b - g_b / h11 - (hess.xbar * (w_new[0, :C] - w[:C])).sum()
+        else:
+            G = suffstats(Xd, z, weight, rows_hint)
+            p = center(G[0], None, C, 1, 0, fit_intercept)
+            w_new = _zeros((1, ldw))
+            call("sglm_ridge_solve_f64", ptr(p.Qc), p.ldq, ptr(p.qc), C, ptr(alphas), 1, ptr(w_new), ldw, ptr(st),
+                 ptr(work), wb, stream_ptr())
+            fetch_scalars([p])
+            b_new = _zeros((1,))
+            if fit_intercept:
+                b_new[0] = p.ybar - float((p.xbar * w_new[0, :C]).sum().item())
         n_iter += 1
         dw = float((w_new[0, :C] - w[:C]).abs().max().item())
         db = float((b_new - b).abs().max().item())
         scale = max(1.0, float(w_new[0, :C].abs().max().item()))
         w_prev, b_prev, f_prev = w, b, f
         w, b = w_new[0].clone(), b_new
-        if max(dw, db) <= step_tol * scale:
+        step = max(dw, db) / scale
+        if use_tc:
+            # linear convergence (inexact Hessian): after a step s that contracted by rho = s / s_prev the iterate is
+            # within s * rho / (1 - rho) of the optimum — stop when that bound is below min(tol, 1e-8)
+            rho = min(step / last_step, 0.9) if np.isfinite(last_step) and last_step > 0 else 1.0
+            if step * rho / (1.0 - min(rho, 0.9)) <= min(tol, 1e-8) or step <= 1e-12:
+                break
+        elif step <= step_tol:
             break
+        refresh = step > 0.2 * last_step          # chord steps must keep contracting by 5x, else a new Hessian
+        last_step = step
     return w[:C].cpu().numpy(), float(b.item()) if fit_intercept else 0.0, n_iter

@@ -53,7 +53,8 @@ __device__ __forceinline__ double z_value(const double *X, long long ldx, const 
 // bit of any element (-> how many radix-128 digits represent the whole column exactly at that scale).
 __global__ void __launch_bounds__(256)
 tc_colmax_kernel(const double *__restrict__ X, long long ldx, const double *__restrict__ Y, long long ldy,
-                 int C, int n_y, long long T, unsigned long long *__restrict__ colmax_bits, int *__restrict__ col_lsb) {
+                 int C, int n_y, long long T, const double *__restrict__ rs,
+                 unsigned long long *__restrict__ colmax_bits, int *__restrict__ col_lsb) {
     const int n_aug = C + n_y + 1;
     const int c = blockIdx.x * 256 + threadIdx.x;
     if (c >= n_aug) return;
@@ -63,7 +64,7 @@ tc_colmax_kernel(const double *__restrict__ X, long long ldx, const double *__re
     bool bad = false;
     int lsb = 0x7fffffff;
     for (long long t = t0; t < t1; ++t) {
-        const double v = fabs(z_value(X, ldx, Y, ldy, C, n_y, t, c));
+        const double v = fabs(z_value(X, ldx, Y, ldy, C, n_y, t, c) * (rs ? rs[t] : 1.0));      // rs: optional row scale (sqrt of a row weight)
         bad |= !(v <= 1.7976931348623157e308);          // NaN or inf
         m = fmax(m, v);
         const long long bits = __double_as_longlong(v);
@@ -95,7 +96,8 @@ __device__ __forceinline__ int digits_needed(double z, int E) {
 
 __global__ void __launch_bounds__(256)
 tc_digits_kernel(const double *__restrict__ X, long long ldx, const double *__restrict__ Y, long long ldy,
-                 int C, int n_y, long long T, const int *__restrict__ colE, int *__restrict__ colS) {
+                 int C, int n_y, long long T, const double *__restrict__ rs, const int *__restrict__ colE,
+                 int *__restrict__ colS) {
     const int n_aug = C + n_y + 1;
     const int c = blockIdx.x * 256 + threadIdx.x;
     if (c >= n_aug) return;
@@ -104,14 +106,14 @@ tc_digits_kernel(const double *__restrict__ X, long long ldx, const double *__re
     const int E = colE[c];
     int need = 1;
     for (long long t = t0; t < t1 && need < TC_SMAX; ++t)
-        need = max(need, digits_needed(z_value(X, ldx, Y, ldy, C, n_y, t, c), E));
+        need = max(need, digits_needed(z_value(X, ldx, Y, ldy, C, n_y, t, c) * (rs ? rs[t] : 1.0), E));
     atomicMax(colS + c, need);
 }
 
 // colS holds the column's lowest set bit on entry (0x7f7f7f7f.. when the column is all zero) and the number
 // of digit planes on exit: digit k carries the bits down to 2^(E - 6 - 7(k-1)), so the column is exact with
 // k >= (E - 6 - lsb) / 7 + 1 planes (the same count the digit-by-digit expansion of every element gives).
-__global__ void tc_exponent_kernel(const unsigned long long *__restrict__ colmax_bits, int n_aug,
+__global__ void tc_exponent_kernel(const unsigned long long *__restrict__ colmax_bits, int n_aug, int max_planes,
                                    int *__restrict__ colE, int *__restrict__ colS, int *__restrict__ flag) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_aug) return;
@@ -125,7 +127,7 @@ __global__ void tc_exponent_kernel(const unsigned long long *__restrict__ colmax
         const int span = E - 6 - lsb;                 // bits below the first digit
         if (span > 0) need = 1 + (span + 6) / 7;
     }
-    colS[c] = min(need, TC_SMAX);
+    colS[c] = min(need, max_planes);      // fewer planes than needed = digits rounded at that plane (approximate Gram)
 }
 
 // ------------------------------------------------------------------ slicing (digits, transposed, gathered rows)
@@ -133,7 +135,7 @@ __global__ void tc_exponent_kernel(const unsigned long long *__restrict__ colmax
 // row lists of all sets (rows[p] < 0 marks padding -> zeros, which the buffer already holds).
 __global__ void __launch_bounds__(256)
 tc_slice_kernel(const double *__restrict__ X, long long ldx, const double *__restrict__ Y, long long ldy,
-                int C, int n_y, const long long *__restrict__ rows, long long n_pos,
+                int C, int n_y, const double *__restrict__ rs, const long long *__restrict__ rows, long long n_pos,
                 const int *__restrict__ colE, const int *__restrict__ colS, const int *__restrict__ plane_row,
                 int8_t *__restrict__ At, long long ld_at) {
     // plane_row[c * TC_SMAX + (k-1)] = row of At holding digit plane k of column c (or -1)
@@ -154,7 +156,7 @@ tc_slice_kernel(const double *__restrict__ X, long long ldx, const double *__res
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
             const long long t = srow[(tid >> 5) + 8 * k];
-            v[k] = (t >= 0 && c < n_aug) ? z_value(X, ldx, Y, ldy, C, n_y, t, c) : 0.0;
+            v[k] = (t >= 0 && c < n_aug) ? z_value(X, ldx, Y, ldy, C, n_y, t, c) * (rs ? rs[t] : 1.0) : 0.0;
         }
 #pragma unroll
         for (int k = 0; k < 16; ++k) tile[cc][(tid >> 5) + 8 * k] = v[k];
@@ -620,9 +622,9 @@ static TcLayout tc_layout(const TcPlan &p, int n_out = 0) {
 
 // Pass 1: per-column exponent and number of digit planes (device arrays colE, colS of n_aug int32;
 // colmax_scratch: n_aug uint64; flag: 1 int32, set when the data contain NaN/inf).
-extern "C" int sglm_gram_tc_analyze_f64(const double *X, int64_t ldx, const double *Y, int64_t ldy, int32_t n_y,
-                                        int64_t T, int32_t C, int32_t *colE, int32_t *colS,
-                                        uint64_t *colmax_scratch, int32_t *flag, void *stream) {
+static int gram_tc_analyze(const double *X, int64_t ldx, const double *Y, int64_t ldy, int32_t n_y, int64_t T,
+                           int32_t C, const double *rs, int max_planes, int32_t *colE, int32_t *colS,
+                           uint64_t *colmax_scratch, int32_t *flag, void *stream) {
     SGLM_CHECK_ARG(T >= 0 && C >= 0 && n_y >= 0 && ldx >= C && ldy >= n_y, SGLM_E_SHAPE, "gram_tc_analyze: bad shape");
     SGLM_CHECK_ARG(colE && colS && colmax_scratch && flag, SGLM_E_INVALID_ARG, "gram_tc_analyze: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
@@ -633,17 +635,35 @@ extern "C" int sglm_gram_tc_analyze_f64(const double *X, int64_t ldx, const doub
     const int gy = (int)std::max<long long>(1, std::min<long long>(T / 256, 64LL * sm_count() / std::max(1, ceil_div(n_aug, 256))));
     dim3 grid(ceil_div(n_aug, 256), gy);
     if (T > 0) {
-        tc_colmax_kernel<<<grid, 256, 0, st>>>(X, ldx, Y, ldy, C, n_y, T, (unsigned long long *)colmax_scratch, colS);
+        tc_colmax_kernel<<<grid, 256, 0, st>>>(X, ldx, Y, ldy, C, n_y, T, rs, (unsigned long long *)colmax_scratch, colS);
         SGLM_LAUNCH_OK("tc_colmax_kernel");
     }
-    tc_exponent_kernel<<<ceil_div(n_aug, 256), 256, 0, st>>>((const unsigned long long *)colmax_scratch, n_aug, colE, colS, flag);
+    tc_exponent_kernel<<<ceil_div(n_aug, 256), 256, 0, st>>>((const unsigned long long *)colmax_scratch, n_aug, max_planes, colE, colS, flag);
     SGLM_LAUNCH_OK("tc_exponent_kernel");
-    if (T > 0 && getenv("SGLM_TC_DIGIT_PASS")) {
+    if (T > 0 && max_planes == TC_SMAX && getenv("SGLM_TC_DIGIT_PASS")) {
         // validation switch: the digit-by-digit second pass (atomicMax on colS) must not raise any count
-        tc_digits_kernel<<<grid, 256, 0, st>>>(X, ldx, Y, ldy, C, n_y, T, colE, colS);
+        tc_digits_kernel<<<grid, 256, 0, st>>>(X, ldx, Y, ldy, C, n_y, T, rs, colE, colS);
         SGLM_LAUNCH_OK("tc_digits_kernel");
     }
     return SGLM_OK;
+}
+
+extern "C" int sglm_gram_tc_analyze_f64(const double *X, int64_t ldx, const double *Y, int64_t ldy, int32_t n_y,
+                                        int64_t T, int32_t C, int32_t *colE, int32_t *colS,
+                                        uint64_t *colmax_scratch, int32_t *flag, void *stream) {
+    return gram_tc_analyze(X, ldx, Y, ldy, n_y, T, C, nullptr, TC_SMAX, colE, colS, colmax_scratch, flag, stream);
+}
+
+// Weighted form: every row t of Z = [X | Y | 1] is scaled by row_scale[t] (= sqrt of a row weight, so that the
+// Gram is Z' diag(w) Z), and at most max_planes (1..8) digit planes are kept per column: with fewer planes than
+// a column needs its digits are rounded at the last plane (relative error 2^-(7 max_planes)) — the approximate
+// Hessian of the Poisson Newton iteration, whose gradient stays exact.
+extern "C" int sglm_gram_tc_analyze_scaled_f64(const double *X, int64_t ldx, const double *Y, int64_t ldy,
+                                               int32_t n_y, int64_t T, int32_t C, const double *row_scale,
+                                               int32_t max_planes, int32_t *colE, int32_t *colS,
+                                               uint64_t *colmax_scratch, int32_t *flag, void *stream) {
+    SGLM_CHECK_ARG(max_planes >= 1 && max_planes <= TC_SMAX, SGLM_E_INVALID_ARG, "gram_tc_analyze_scaled: max_planes out of range");
+    return gram_tc_analyze(X, ldx, Y, ldy, n_y, T, C, row_scale, max_planes, colE, colS, colmax_scratch, flag, stream);
 }
 
 extern "C" size_t sglm_gram_tc_workspace_bytes(int32_t n_aug, const int32_t *colS_host, int32_t n_sets,
@@ -672,7 +692,7 @@ static int gram_tc_run(const double *X, int64_t ldx, const double *Y, int64_t ld
                        int32_t C, const int32_t *colE, const int32_t *colS, const int32_t *colS_host,
                        int32_t n_sets, const int64_t *set_rows_host, const int64_t *rows, int32_t n_out,
                        const int32_t *member_host, double *G, int64_t ldg, void *workspace, size_t workspace_bytes,
-                       int32_t use_check_gemm, void *stream);
+                       int32_t use_check_gemm, void *stream, const double *rs = nullptr);
 
 extern "C" int sglm_gram_tc_f64(const double *X, int64_t ldx, const double *Y, int64_t ldy, int32_t n_y, int64_t T,
                                 int32_t C, const int32_t *colE, const int32_t *colS, const int32_t *colS_host,
@@ -681,6 +701,16 @@ extern "C" int sglm_gram_tc_f64(const double *X, int64_t ldx, const double *Y, i
                                 void *stream) {
     return gram_tc_run(X, ldx, Y, ldy, n_y, T, C, colE, colS, colS_host, n_sets, set_rows_host, rows, 0, nullptr, G, ldg,
                        workspace, workspace_bytes, use_check_gemm, stream);
+}
+
+// Weighted Gram Z' diag(row_scale^2) Z with the planes chosen by sglm_gram_tc_analyze_scaled_f64.
+extern "C" int sglm_gram_tc_scaled_f64(const double *X, int64_t ldx, const double *Y, int64_t ldy, int32_t n_y,
+                                       int64_t T, int32_t C, const double *row_scale, const int32_t *colE,
+                                       const int32_t *colS, const int32_t *colS_host, int32_t n_sets,
+                                       const int64_t *set_rows_host, const int64_t *rows, double *G, int64_t ldg,
+                                       void *workspace, size_t workspace_bytes, void *stream) {
+    return gram_tc_run(X, ldx, Y, ldy, n_y, T, C, colE, colS, colS_host, n_sets, set_rows_host, rows, 0, nullptr, G, ldg,
+                       workspace, workspace_bytes, 0, stream, row_scale);
 }
 
 extern "C" size_t sglm_gram_tc_cells_workspace_bytes(int32_t n_aug, const int32_t *colS_host, int32_t n_cells,
@@ -708,7 +738,7 @@ static int gram_tc_run(const double *X, int64_t ldx, const double *Y, int64_t ld
                        int32_t C, const int32_t *colE, const int32_t *colS, const int32_t *colS_host,
                        int32_t n_sets, const int64_t *set_rows_host, const int64_t *rows, int32_t n_out,
                        const int32_t *member_host, double *G, int64_t ldg, void *workspace, size_t workspace_bytes,
-                       int32_t use_check_gemm, void *stream) {
+                       int32_t use_check_gemm, void *stream, const double *rs) {
     const int n_aug = C + n_y + 1;
     SGLM_CHECK_ARG(T >= 0 && C >= 0 && n_y >= 0 && n_sets >= 1 && ldx >= C && ldy >= n_y && ldg >= n_aug, SGLM_E_SHAPE,
                    "gram_tc: bad shape");
@@ -751,7 +781,7 @@ static int gram_tc_run(const double *X, int64_t ldx, const double *Y, int64_t ld
     SGLM_CUDA_OK(cudaStreamSynchronize(st));        // the pageable host vectors above die with this frame
 
     dim3 sgrid((unsigned)(p.n_pos / 128), (unsigned)ceil_div(n_aug, 32));
-    tc_slice_kernel<<<sgrid, 256, 0, st>>>(X, ldx, Y, ldy, C, n_y, (const long long *)rows, p.n_pos, colE, colS,
+    tc_slice_kernel<<<sgrid, 256, 0, st>>>(X, ldx, Y, ldy, C, n_y, rs, (const long long *)rows, p.n_pos, colE, colS,
                                            d_plane, At, p.n_pos);
     SGLM_LAUNCH_OK("tc_slice_kernel");
 

@@ -126,6 +126,44 @@ finish_sums_kernel(const double *__restrict__ partials, int n_part, double *__re
     }
 }
 
+// out[c] = sum_t X[t][c] * r[t]  (the exact gradient X'r of the Poisson Newton iteration): every CTA owns a
+// contiguous range of rows, a thread owns columns tid, tid + 256, ... (coalesced row reads, r[t] broadcast),
+// per-CTA partial sums are added by xt_finish_kernel in fixed order (deterministic).
+constexpr int XT_COLS = 4;
+__global__ void __launch_bounds__(PR_THREADS)
+xt_vec_kernel(const double *__restrict__ X, long long ldx, const double *__restrict__ r, long long T, int C,
+              double *__restrict__ partials) {
+    const long long rows_per = (T + gridDim.x - 1) / gridDim.x;
+    const long long t0 = (long long)blockIdx.x * rows_per, t1 = min(T, t0 + rows_per);
+    for (int c0 = 0; c0 < C; c0 += PR_THREADS * XT_COLS) {
+        double acc[XT_COLS];
+#pragma unroll
+        for (int j = 0; j < XT_COLS; ++j) acc[j] = 0.0;
+        for (long long t = t0; t < t1; ++t) {
+            const double rv = r[t];
+            if (rv == 0.0) continue;                       // rows outside the fold (uniform per CTA row)
+            const double *row = X + t * ldx + c0 + threadIdx.x;
+#pragma unroll
+            for (int j = 0; j < XT_COLS; ++j)
+                if (c0 + threadIdx.x + j * PR_THREADS < C) acc[j] = fma(__ldcs(row + j * PR_THREADS), rv, acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < XT_COLS; ++j) {
+            const int c = c0 + threadIdx.x + j * PR_THREADS;
+            if (c < C) partials[(long long)blockIdx.x * C + c] = acc[j];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+xt_finish_kernel(const double *__restrict__ partials, int n_part, int C, double *__restrict__ out) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0;
+    for (int i = 0; i < n_part; ++i) s += partials[(long long)i * C + c];
+    out[c] = s;
+}
+
 static int pass_grid(long long T) {
     long long want = ceil_div<long long>(std::max<long long>(T, 1), PR_WARPS);
     return (int)std::min<long long>(want, std::min<long long>(PR_MAX_GRID, (long long)sm_count() * 8));
@@ -185,5 +223,22 @@ extern "C" int sglm_poisson_irls_prepare_f64(const double *X, int64_t ldx, const
     SGLM_LAUNCH_OK("row_pass_kernel<irls>");
     finish_sums_kernel<<<1, 256, 0, st>>>((const double *)workspace, grid, sums);
     SGLM_LAUNCH_OK("finish_sums_kernel");
+    return SGLM_OK;
+}
+
+extern "C" size_t sglm_xt_vec_workspace_bytes(int32_t C) { return (size_t)sm_count() * 8 * (size_t)std::max(C, 1) * sizeof(double); }
+
+// out[c] = sum_t X[t][c] r[t]: one streaming pass over X (8*T*C bytes), deterministic.
+extern "C" int sglm_xt_vec_f64(const double *X, int64_t ldx, const double *r, int64_t T, int32_t C, double *out,
+                               void *workspace, size_t workspace_bytes, void *stream) {
+    SGLM_CHECK_ARG(T >= 0 && C > 0 && ldx >= C, SGLM_E_SHAPE, "xt_vec: bad shape");
+    SGLM_CHECK_ARG(X && r && out && workspace, SGLM_E_INVALID_ARG, "xt_vec: null pointer");
+    SGLM_CHECK_ARG(workspace_bytes >= sglm_xt_vec_workspace_bytes(C), SGLM_E_WORKSPACE, "xt_vec: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((long long)sm_count() * 8, (T + 63) / 64));
+    xt_vec_kernel<<<grid, PR_THREADS, 0, st>>>(X, ldx, r, T, C, (double *)workspace);
+    SGLM_LAUNCH_OK("xt_vec_kernel");
+    xt_finish_kernel<<<ceil_div(C, 256), 256, 0, st>>>((const double *)workspace, grid, C, out);
+    SGLM_LAUNCH_OK("xt_finish_kernel");
     return SGLM_OK;
 }

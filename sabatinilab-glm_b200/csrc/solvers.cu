@@ -574,6 +574,70 @@ ridge_cholesky_kernel(const double *__restrict__ Qc, long long ldq, const double
     if (tid == 0) status[kq] = bad;
 }
 
+// --------------------------------------------------------------------------- solve with a stored Cholesky factor
+// L L' x = rhs with the lower-triangular factor that ridge_cholesky_kernel leaves in its work buffer
+// (row-major, L[i][j] for j <= i).  One CTA: blocked forward substitution (32 unknowns by one warp, then
+// every thread corrects its rows with 32 contiguous factor entries) and blocked back substitution
+// (column access of L is contiguous across threads).  Used by the Poisson Newton iteration to reuse a
+// Hessian factor over several steps (chord iterations): 2 * C^2/2 * 8 bytes of factor traffic per solve.
+__global__ void __launch_bounds__(RC_THREADS)
+chol_solve_kernel(const double *__restrict__ L, long long ldq, int C, const double *__restrict__ rhs,
+                  double *__restrict__ out) {
+    extern __shared__ __align__(16) double sh[];
+    double *D = sh;                          // [32][33] diagonal block
+    double *xv = D + RC_NB * 33;             // [C] running right-hand side / solution
+    const int tid = threadIdx.x;
+    for (int j = tid; j < C; j += RC_THREADS) xv[j] = rhs[j];
+    __syncthreads();
+    const int n_blk = (C + RC_NB - 1) / RC_NB;
+    for (int b = 0; b < n_blk; ++b) {                       // forward: L y = rhs
+        const int k0 = b * RC_NB, nb = min(RC_NB, C - k0);
+        for (int e = tid; e < nb * nb; e += RC_THREADS) {
+            const int r = e / nb, c = e - r * nb;
+            D[r * 33 + c] = (c <= r) ? L[(long long)(k0 + r) * ldq + k0 + c] : 0.0;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int c = 0; c < nb; ++c) {
+                double s = xv[k0 + c];
+                for (int r = 0; r < c; ++r) s -= D[c * 33 + r] * xv[k0 + r];
+                xv[k0 + c] = s / D[c * 33 + c];
+            }
+        }
+        __syncthreads();
+        for (int i = k0 + nb + tid; i < C; i += RC_THREADS) {
+            const double *row = L + (long long)i * ldq + k0;
+            double s = xv[i];
+            for (int c = 0; c < nb; ++c) s -= row[c] * xv[k0 + c];
+            xv[i] = s;
+        }
+        __syncthreads();
+    }
+    for (int b = n_blk - 1; b >= 0; --b) {                  // backward: L' x = y
+        const int k0 = b * RC_NB, nb = min(RC_NB, C - k0);
+        for (int e = tid; e < nb * nb; e += RC_THREADS) {
+            const int r = e / nb, c = e - r * nb;
+            D[r * 33 + c] = (c <= r) ? L[(long long)(k0 + r) * ldq + k0 + c] : 0.0;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int c = nb - 1; c >= 0; --c) {
+                double s = xv[k0 + c];
+                for (int r = c + 1; r < nb; ++r) s -= D[r * 33 + c] * xv[k0 + r];
+                xv[k0 + c] = s / D[c * 33 + c];
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < k0; i += RC_THREADS) {
+            double s = xv[i];
+            for (int r = 0; r < nb; ++r) s -= L[(long long)(k0 + r) * ldq + i] * xv[k0 + r];
+            xv[i] = s;
+        }
+        __syncthreads();
+    }
+    for (int j = tid; j < C; j += RC_THREADS) out[j] = xv[j];
+}
+
 // --------------------------------------------------------------------------- intercept + evaluation vectors
 __global__ void __launch_bounds__(128)
 finalize_models_kernel(const double *__restrict__ W, long long ldw, int C, int n_y,
@@ -796,5 +860,20 @@ static int quadform_launch(const double *A, int64_t lda, int32_t n, const double
         quadform_kernel<4><<<dim3(ceil_div(n_models, 4), n_splits), QF_THREADS, smem, (cudaStream_t)stream>>>(A, lda, n, V, ldv, n_models, out);
     }
     SGLM_LAUNCH_OK("quadform_kernel");
+    return SGLM_OK;
+}
+
+// x = (L L')^-1 rhs with the factor of system `k` that sglm_ridge_solve_f64 left in its work buffer
+// (work + k * (C + 1) * ldq doubles).  Replaces a second factorisation when the matrix has not changed.
+extern "C" int sglm_chol_solve_f64(const void *work, int64_t ldq, int32_t C, int32_t k, const double *rhs, double *out,
+                                   void *stream) {
+    SGLM_CHECK_ARG(C > 0 && ldq >= C && k >= 0, SGLM_E_SHAPE, "chol_solve: bad shape");
+    SGLM_CHECK_ARG(work && rhs && out, SGLM_E_INVALID_ARG, "chol_solve: null pointer");
+    const size_t smem = (size_t)(RC_NB * 33 + C) * sizeof(double);
+    SGLM_CHECK_ARG(smem <= 227 * 1024, SGLM_E_UNSUPPORTED, "chol_solve: C=%d too large for shared memory", C);
+    SGLM_CUDA_OK(cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const double *L = (const double *)work + (size_t)k * (size_t)(C + 1) * (size_t)ldq;
+    chol_solve_kernel<<<1, RC_THREADS, smem, (cudaStream_t)stream>>>(L, ldq, C, rhs, out);
+    SGLM_LAUNCH_OK("chol_solve_kernel");
     return SGLM_OK;
 }

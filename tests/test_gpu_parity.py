@@ -620,6 +620,38 @@ def test_config4_poisson_alpha_sweep_vs_sklearn_optimum():
         assert abs(g.r2_score(Xd, y) - ref.score(Xd, y)) < 1e-6
 
 
+def test_poisson_newton_with_tensor_core_hessian_reaches_the_same_optimum():
+    """The large-problem Poisson path: Newton steps whose Hessian X'WX is the tcgen05 digit-plane Gram of
+    sqrt(W) X truncated to 4 planes (approximate) and whose gradient X'(mu - y) is exact.  Same optimum as
+    TweedieRegressor driven to convergence and as the exact fp64 IRLS path, with and without fold weights."""
+    from sklearn.linear_model import TweedieRegressor
+    X0, shifts, Xd, y = _session(15_000, 20, 20, 19, 404, poisson=True)
+    Xg, yg = torch.from_numpy(Xd).cuda(), torch.from_numpy(y).cuda()
+    rng = np.random.default_rng(1)
+    rw_h = (rng.random(Xd.shape[0]) < 0.8).astype(np.float64)
+    rw = torch.from_numpy(rw_h).cuda()
+    old = eng.POISSON_TC
+    try:
+        for alpha, weights in [(1e-2, None), (1.0, None), (1e-2, rw)]:
+            eng.POISSON_TC = True
+            w_tc, b_tc, n_tc = eng.poisson_irls(Xg, yg, alpha, True, weights)
+            eng.POISSON_TC = False
+            w_ex, b_ex, n_ex = eng.poisson_irls(Xg, yg, alpha, True, weights)
+            assert coef_rel_err(w_tc, w_ex) < 1e-7 and abs(b_tc - b_ex) < 1e-8
+            assert n_tc <= n_ex + 3
+            sel = slice(None) if weights is None else rw_h > 0
+            ref = TweedieRegressor(power=1, alpha=alpha, solver="newton-cholesky", tol=1e-12, max_iter=1000).fit(Xd[sel], y[sel])
+            assert coef_rel_err(w_tc, ref.coef_) < 1e-6
+            assert abs(b_tc - ref.intercept_) < 1e-7
+        eng.POISSON_TC = True
+        w0, b0, _ = eng.poisson_irls(Xg, yg, 0.1, False, None)               # no intercept
+        ref = TweedieRegressor(power=1, alpha=0.1, fit_intercept=False, solver="newton-cholesky", tol=1e-12,
+                               max_iter=1000).fit(Xd, y)
+        assert coef_rel_err(w0, ref.coef_) < 1e-6 and b0 == 0.0
+    finally:
+        eng.POISSON_TC = old
+
+
 def test_full_size_properties_config2_and_3():
     """Size-independent properties at (near) BASELINE sizes, checked with an independent fp64
     implementation (torch): Ridge normal equations hold; ElasticNet models satisfy the duality-gap
