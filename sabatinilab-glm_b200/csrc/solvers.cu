@@ -10,6 +10,7 @@
 // per model = 8*C per coordinate update that changes w (one row of Q) — the kernel counts
 // those updates (info[6m+3]) so bench.py can report sum(bytes)/time.
 #include <algorithm>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -108,6 +109,10 @@ __device__ __forceinline__ void cta_reduce(double (&v)[K], double *scratch) {
 __device__ __forceinline__ void cd_cp_async8(void *smem, const void *gmem) {
     unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cd_cp_async16(void *smem, const void *gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
 }
 __device__ __forceinline__ void cd_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cd_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
@@ -574,6 +579,186 @@ ridge_cholesky_kernel(const double *__restrict__ Qc, long long ldq, const double
     if (tid == 0) status[kq] = bad;
 }
 
+// --------------------------------------------------------------------------- Cholesky, left-looking form
+// Same system and outputs as ridge_cholesky_kernel.  The right-looking form rewrites the whole trailing
+// matrix after every 32-column panel (C^3/(3*32) * 16 bytes of global traffic per system: 0.9 GB at
+// C = 1220, 35 ms with 120 systems in flight — scripts/c2_timeline.py); here a block column is brought up
+// to date ONCE from the factor columns to its left (reads only: C^3/(6*32) * 8 bytes), factored and never
+// touched again.  Row tiles of 256 rows x 32 columns, 8 x 4 accumulators per thread, the rhs travels as
+// row C (forward substitution for free), back substitution as before.
+constexpr int LL_RT = 256;      // rows per tile
+
+constexpr int LL_LD = 34;       // padded row length of the staged factor tiles (16-byte aligned rows)
+
+__global__ void __launch_bounds__(RC_THREADS)
+ridge_cholesky_ll_kernel(const double *__restrict__ Qc, long long ldq, const double *__restrict__ qc, int C,
+                         const double *__restrict__ alpha, double *__restrict__ W, long long ldw,
+                         int *__restrict__ status, double *__restrict__ work) {
+    extern __shared__ __align__(16) double sh[];
+    double *D = sh;                                  // [32][33] diagonal block (steps 2, 3, back substitution)
+    double *LJ = D + RC_NB * 33;                     // [2][32][34] factor rows of the block column, double buffered
+    double *LI = LJ + 2 * RC_NB * LL_LD;             // [2][256][34] factor rows of the row tile, double buffered
+    double *wv = LI + 2 * LL_RT * LL_LD;             // [C] solution vector
+    __shared__ int bad;
+
+    const int kq = blockIdx.x, tid = threadIdx.x;
+    const double a = alpha[kq];
+    double *M = work + (long long)kq * (C + 1) * ldq;
+    if (tid == 0) bad = 0;
+    const int ty = tid >> 3, tx = tid & 7;      // rows ty + 32u (u < 8), columns tx + 8v (v < 4)
+    const bool al16 = ((ldq & 1) == 0) && ((reinterpret_cast<uintptr_t>(M) & 15) == 0);
+
+    for (int j0 = 0; j0 < C; j0 += RC_NB) {
+        const int nb = min(RC_NB, C - j0);
+        // 1. block column j0: A[i][c] = M0[i][j0+c] - sum_{k<j0} L[i][k] L[j0+c][k]  for rows i = j0..C (row C = rhs)
+        for (int i0 = j0; i0 <= C; i0 += LL_RT) {
+            double acc[8][4];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const int i = i0 + ty + 32 * u, c = tx + 8 * v, j = j0 + c;
+                    double x = 0.0;
+                    if (c < nb && i <= C) {
+                        if (i == C) x = qc[j];
+                        else if (j <= i) x = Qc[(long long)i * ldq + j] + (i == j ? a : 0.0);
+                    }
+                    acc[u][v] = x;
+                }
+            // asynchronous staging of the factor rows of chunk k0 (16-byte copies; rows past C are zero)
+            auto stage = [&](int k0, int buf) {
+                double *li = LI + buf * LL_RT * LL_LD, *lj = LJ + buf * RC_NB * LL_LD;
+                for (int e = tid; e < (LL_RT + RC_NB) * 16; e += RC_THREADS) {
+                    const int r = e >> 4, ch = (e & 15) * 2;
+                    const bool isj = r >= LL_RT;
+                    const int row = isj ? j0 + (r - LL_RT) : i0 + r;
+                    double *dst = isj ? lj + (r - LL_RT) * LL_LD + ch : li + r * LL_LD + ch;
+                    const bool ok = isj ? (r - LL_RT) < nb : row <= C;
+                    if (ok && al16) {
+                        cd_cp_async16(dst, M + (long long)row * ldq + k0 + ch);
+                    } else if (ok) {
+                        dst[0] = M[(long long)row * ldq + k0 + ch];
+                        dst[1] = M[(long long)row * ldq + k0 + ch + 1];
+                    } else {
+                        dst[0] = 0.0; dst[1] = 0.0;
+                    }
+                }
+                cd_cp_async_commit();
+            };
+            __syncthreads();                                   // previous tile / step done with the buffers
+            int buf = 0;
+            if (j0 > 0) stage(0, 0);
+            for (int k0 = 0; k0 < j0; k0 += RC_NB) {
+                const bool more = k0 + RC_NB < j0;
+                if (more) stage(k0 + RC_NB, buf ^ 1);
+                if (more) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+                else cd_cp_async_wait_all();
+                __syncthreads();
+                const double *li = LI + buf * LL_RT * LL_LD, *lj = LJ + buf * RC_NB * LL_LD;
+#pragma unroll 4
+                for (int c = 0; c < RC_NB; ++c) {
+                    double pa[8], pb[4];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) pa[u] = li[(ty + 32 * u) * LL_LD + c];
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) pb[v] = lj[(tx + 8 * v) * LL_LD + c];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) acc[u][v] -= pa[u] * pb[v];
+                }
+                __syncthreads();                               // buffer `buf` may be refilled by the next stage()
+                buf ^= 1;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const int i = i0 + ty + 32 * u, c = tx + 8 * v;
+                    if (c < nb && i <= C && (i == C || j0 + c <= i)) M[(long long)i * ldq + j0 + c] = acc[u][v];
+                }
+        }
+        __syncthreads();
+        // 2. diagonal block -> smem, unblocked Cholesky by warp 0
+        for (int e = tid; e < nb * nb; e += RC_THREADS) {
+            const int r = e / nb, c = e - r * nb;
+            D[r * 33 + c] = (c <= r) ? M[(long long)(j0 + r) * ldq + j0 + c] : 0.0;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            for (int c = 0; c < nb; ++c) {
+                double d = D[c * 33 + c];
+                if (!(d > 0.0)) { if (tid == 0) bad = 1; d = nan(""); }
+                const double l = sqrt(d);
+                __syncwarp();
+                if (tid == 0) D[c * 33 + c] = l;
+                for (int r = c + 1 + tid; r < nb; r += 32) D[r * 33 + c] /= l;
+                __syncwarp();
+                for (int e = tid; e < nb * nb; e += 32) {
+                    const int r = e / nb, cc = e - r * nb;
+                    if (cc > c && cc <= r) D[r * 33 + cc] -= D[r * 33 + c] * D[cc * 33 + c];
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < nb * nb; e += RC_THREADS) {
+            const int r = e / nb, c = e - r * nb;
+            if (c <= r) M[(long long)(j0 + r) * ldq + j0 + c] = D[r * 33 + c];
+        }
+        // 3. panel solve: rows below the block (incl. the rhs row C): x L_jj' = A[i, :]
+        for (int i = j0 + nb + tid; i <= C; i += RC_THREADS) {
+            double x[RC_NB];
+            double *row = M + (long long)i * ldq + j0;
+#pragma unroll
+            for (int c = 0; c < RC_NB; ++c) x[c] = (c < nb) ? row[c] : 0.0;
+#pragma unroll
+            for (int c = 0; c < RC_NB; ++c) {
+                if (c < nb) {
+                    double sv = x[c];
+#pragma unroll
+                    for (int r = 0; r < RC_NB; ++r)
+                        if (r < c) sv -= x[r] * D[c * 33 + r];
+                    x[c] = sv / D[c * 33 + c];
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < RC_NB; ++c)
+                if (c < nb) row[c] = x[c];
+        }
+        __syncthreads();
+    }
+
+    // row C now holds y with L y = qc.  Back substitution L' w = y, blocked from the end.
+    for (int j = tid; j < C; j += RC_THREADS) wv[j] = M[(long long)C * ldq + j];
+    __syncthreads();
+    const int n_blk = (C + RC_NB - 1) / RC_NB;
+    for (int b = n_blk - 1; b >= 0; --b) {
+        const int k0 = b * RC_NB, nb = min(RC_NB, C - k0);
+        for (int e = tid; e < nb * nb; e += RC_THREADS) {
+            const int r = e / nb, c = e - r * nb;
+            D[r * 33 + c] = (c <= r) ? M[(long long)(k0 + r) * ldq + k0 + c] : 0.0;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int c = nb - 1; c >= 0; --c) {
+                double sv = wv[k0 + c];
+                for (int r = c + 1; r < nb; ++r) sv -= D[r * 33 + c] * wv[k0 + r];
+                wv[k0 + c] = sv / D[c * 33 + c];
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < k0; i += RC_THREADS) {
+            double sv = wv[i];
+            for (int r = 0; r < nb; ++r) sv -= M[(long long)(k0 + r) * ldq + i] * wv[k0 + r];
+            wv[i] = sv;
+        }
+        __syncthreads();
+    }
+    for (int j = tid; j < C; j += RC_THREADS) W[(long long)kq * ldw + j] = wv[j];
+    if (tid == 0) status[kq] = bad;
+}
+
 // --------------------------------------------------------------------------- solve with a stored Cholesky factor
 // L L' x = rhs with the lower-triangular factor that ridge_cholesky_kernel leaves in its work buffer
 // (row-major, L[i][j] for j <= i).  One CTA: blocked forward substitution (32 unknowns by one warp, then
@@ -804,12 +989,22 @@ extern "C" int sglm_ridge_solve_f64(const double *Qc, int64_t ldq, const double 
     SGLM_CHECK_ARG(Qc && qc && alpha && W && status && work, SGLM_E_INVALID_ARG, "ridge_solve: null pointer");
     SGLM_CHECK_ARG(work_bytes >= sglm_ridge_workspace_bytes(C, ldq, n_alpha), SGLM_E_WORKSPACE,
                    "ridge_solve: workspace too small");
-    const size_t smem = (size_t)(RC_NB * 33 + 2 * 64 * 33 + C) * sizeof(double);
+    const char *form = getenv("SGLM_CHOLESKY");             // "right": the first right-looking kernel (A/B switch)
+    if (form && form[0] == 'r') {
+        const size_t smem = (size_t)(RC_NB * 33 + 2 * 64 * 33 + C) * sizeof(double);
+        SGLM_CHECK_ARG(smem <= 227 * 1024, SGLM_E_UNSUPPORTED, "ridge_solve: C=%d too large for shared memory", C);
+        SGLM_CUDA_OK(cudaFuncSetAttribute(ridge_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ridge_cholesky_kernel<<<n_alpha, RC_THREADS, smem, (cudaStream_t)stream>>>(Qc, ldq, qc, C, alpha, W, ldw, status,
+                                                                                  (double *)work);
+        SGLM_LAUNCH_OK("ridge_cholesky_kernel");
+        return SGLM_OK;
+    }
+    const size_t smem = (size_t)(RC_NB * 33 + 2 * RC_NB * LL_LD + 2 * LL_RT * LL_LD + C) * sizeof(double);
     SGLM_CHECK_ARG(smem <= 227 * 1024, SGLM_E_UNSUPPORTED, "ridge_solve: C=%d too large for shared memory", C);
-    SGLM_CUDA_OK(cudaFuncSetAttribute(ridge_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ridge_cholesky_kernel<<<n_alpha, RC_THREADS, smem, (cudaStream_t)stream>>>(Qc, ldq, qc, C, alpha, W, ldw, status,
-                                                                              (double *)work);
-    SGLM_LAUNCH_OK("ridge_cholesky_kernel");
+    SGLM_CUDA_OK(cudaFuncSetAttribute(ridge_cholesky_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ridge_cholesky_ll_kernel<<<n_alpha, RC_THREADS, smem, (cudaStream_t)stream>>>(Qc, ldq, qc, C, alpha, W, ldw, status,
+                                                                                 (double *)work);
+    SGLM_LAUNCH_OK("ridge_cholesky_ll_kernel");
     return SGLM_OK;
 }
 
