@@ -442,24 +442,45 @@ tc_gram_i8_check_kernel(const int8_t *__restrict__ At, long long ld_at, const in
 // overlap (the full data contain every test fold, random folds intersect), so the GEMM runs once over the
 // disjoint CELLS of the partition they induce and the Gram of each set is the sum of its cells' Grams.
 constexpr int TC_SUM_OUT = 8;      // output sets accumulated per pass over the cells
+constexpr int TC_SUM_CELLS = 256;  // cells whose membership masks are staged in shared memory
 __global__ void __launch_bounds__(256)
 tc_cell_sum_kernel(const long long *__restrict__ SG, long long n_elem, int n_cells, const int *__restrict__ member,
                    int n_out, long long *__restrict__ SGout) {
-    // every cell element is read once per group of TC_SUM_OUT output sets and added to the sets it belongs to
-    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < n_elem; e += (long long)gridDim.x * 256) {
-        for (int o0 = 0; o0 < n_out; o0 += TC_SUM_OUT) {
-            long long acc[TC_SUM_OUT];
+    // every cell element is read once per group of TC_SUM_OUT output sets and added to the sets it belongs to;
+    // membership of a cell = one bit mask per group (shared memory), two elements per thread, cells unrolled by 4
+    __shared__ unsigned smask[TC_SUM_CELLS];
+    for (int o0 = 0; o0 < n_out; o0 += TC_SUM_OUT) {
+        __syncthreads();
+        for (int c = threadIdx.x; c < n_cells && c < TC_SUM_CELLS; c += 256) {
+            unsigned m = 0;
+            for (int k = 0; k < TC_SUM_OUT && o0 + k < n_out; ++k)
+                if (member[(o0 + k) * n_cells + c]) m |= 1u << k;
+            smask[c] = m;
+        }
+        __syncthreads();
+        for (long long e = ((long long)blockIdx.x * 256 + threadIdx.x) * 2; e < n_elem; e += (long long)gridDim.x * 512) {
+            const bool two = e + 1 < n_elem;
+            long long a0[TC_SUM_OUT], a1[TC_SUM_OUT];
 #pragma unroll
-            for (int k = 0; k < TC_SUM_OUT; ++k) acc[k] = 0;
+            for (int k = 0; k < TC_SUM_OUT; ++k) { a0[k] = 0; a1[k] = 0; }
+#pragma unroll 4
             for (int c = 0; c < n_cells; ++c) {
-                const long long v = SG[(long long)c * n_elem + e];
+                const long long *src = SG + (long long)c * n_elem + e;
+                long long v0, v1 = 0;
+                if (two) { const longlong2 v = *reinterpret_cast<const longlong2 *>(src); v0 = v.x; v1 = v.y; }
+                else v0 = src[0];
+                const unsigned m = smask[c];
 #pragma unroll
                 for (int k = 0; k < TC_SUM_OUT; ++k)
-                    if (o0 + k < n_out && member[(o0 + k) * n_cells + c]) acc[k] += v;
+                    if ((m >> k) & 1u) { a0[k] += v0; a1[k] += v1; }
             }
 #pragma unroll
             for (int k = 0; k < TC_SUM_OUT; ++k)
-                if (o0 + k < n_out) SGout[(long long)(o0 + k) * n_elem + e] = acc[k];
+                if (o0 + k < n_out) {
+                    long long *dst = SGout + (long long)(o0 + k) * n_elem + e;
+                    dst[0] = a0[k];
+                    if (two) dst[1] = a1[k];
+                }
         }
     }
 }
@@ -730,6 +751,7 @@ extern "C" int sglm_gram_tc_cells_f64(const double *X, int64_t ldx, const double
                                       int64_t ldg, void *workspace, size_t workspace_bytes, int32_t use_check_gemm,
                                       void *stream) {
     SGLM_CHECK_ARG(n_out >= 1 && member_host, SGLM_E_INVALID_ARG, "gram_tc_cells: membership table missing");
+    SGLM_CHECK_ARG(n_cells <= TC_SUM_CELLS, SGLM_E_UNSUPPORTED, "gram_tc_cells: at most %d cells", TC_SUM_CELLS);
     return gram_tc_run(X, ldx, Y, ldy, n_y, T, C, colE, colS, colS_host, n_cells, cell_rows_host, rows, n_out,
                        member_host, G, ldg, workspace, workspace_bytes, use_check_gemm, stream);
 }
