@@ -45,7 +45,7 @@ constexpr int RS = 40;     // doubles per (record, model): 32 deltas + zeros tha
 
 struct Layout {
     int NBLK, BPC, CoP;
-    size_t w, Qw, blk, qd, rdelta, rmask, full, bbar, xch, par, act, drp, pdone, ccnt, total;
+    size_t w, Qw, blk, qd, rdelta, rmask, full, bbar, xch, par, act, drp, pdone, ccnt, pmv, total;
 };
 
 __host__ __device__ inline Layout make_layout(int M, int K, int NB, int C) {
@@ -68,6 +68,7 @@ __host__ __device__ inline Layout make_layout(int M, int K, int NB, int C) {
     L.drp = o;    o += (size_t)M * L.NBLK * 4;
     L.pdone = o;  o += (size_t)NB * 4;
     L.ccnt = o;   o += (size_t)K * NB * 4;      // records completed per (CTA, panel warp) of the cluster
+    L.pmv = o;    o += (size_t)M * L.NBLK;                // coordinates moved per (model, block) in the last sweep
     L.total = (o + 15) & ~(size_t)15;
     return L;
 }
@@ -196,6 +197,7 @@ enet_cd_cluster_kernel(const double *const *__restrict__ prob_Q, const double *c
     unsigned *drp = reinterpret_cast<unsigned *>(smraw + L.drp);    // [M][NBLK]
     unsigned *pdone = reinterpret_cast<unsigned *>(smraw + L.pdone);
     unsigned *ccnt = reinterpret_cast<unsigned *>(smraw + L.ccnt);
+    unsigned char *pmv = smraw + L.pmv;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned rank = (K > 1) ? cluster_rank() : 0u;
@@ -253,6 +255,7 @@ enet_cd_cluster_kernel(const double *const *__restrict__ prob_Q, const double *c
         const int rem = C - (b << 5);
         act[i] = ((alive >> mm) & 1u) ? (rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u)) : 0u;
         drp[i] = 0u;
+        pmv[i] = 0;
     }
     cluster_sync_all();           // barriers initialised cluster-wide before any remote arrive
 
@@ -505,33 +508,43 @@ enet_cd_cluster_kernel(const double *const *__restrict__ prob_Q, const double *c
                     const double a_l = fma(w_l, d_l, q_l);
                     const double negw = ok_l ? -w_l : 0.0;
                     const double k_pos = ok_l ? fma(-l1, inv_l, -w_l) : 0.0, k_neg = ok_l ? fma(l1, inv_l, -w_l) : 0.0;
-                    if (__popc(mask) >= 12) {
-                        // straight-line: a screened-out coordinate contributes delta = 0 (exact no-op FMAs)
+                    // Candidates of all 32 lanes from the current state; lanes whose candidate is zero need no
+                    // turn (see solvers.cu): dense blocks run the straight 32-step chain, sparse ones jump from
+                    // mover to mover.
+                    auto candidate = [&]() -> double {
+                        const double rr = a_l - Qw_l;
+                        const double dpos = fma(rr, inv_l, k_pos), dneg = fma(rr, inv_l, k_neg);
+                        return (rr > l1) ? dpos : ((rr < -l1) ? dneg : negw);
+                    };
+                    if (pmv[m * NBLK + b] >= 20) {
+                        // dense block (20+ coordinates moved in the last sweep): straight-line, a screened-out
+                        // coordinate contributes delta = 0 (exact no-op FMAs), no vote on the dependent path
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             const double s_il = S[i * 32 + lane];
-                            const double rr = a_l - Qw_l;
-                            const double dpos = fma(rr, inv_l, k_pos), dneg = fma(rr, inv_l, k_neg);
-                            const double dc = (rr > l1) ? dpos : ((rr < -l1) ? dneg : negw);
+                            const double dc = candidate();
                             const double di = __shfl_sync(0xffffffffu, dc, i);
                             if (lane == i) delta_l = dc;
                             Qw_l = fma(di, s_il, Qw_l);
                         }
                     } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            if (!((mask >> i) & 1u)) continue;                // uniform: coordinate screened out
-                            const double s_il = S[i * 32 + lane];
-                            const double rr = a_l - Qw_l;
-                            const double dpos = fma(rr, inv_l, k_pos), dneg = fma(rr, inv_l, k_neg);
-                            const double dc = (rr > l1) ? dpos : ((rr < -l1) ? dneg : negw);
+                        double dc = candidate();
+                        unsigned todo = mask;
+                        while (true) {
+                            const unsigned mv = __ballot_sync(0xffffffffu, dc != 0.0) & todo;
+                            if (!mv) break;
+                            const int i = __ffs(mv) - 1;
                             const double di = __shfl_sync(0xffffffffu, dc, i);
                             if (lane == i) delta_l = dc;
-                            Qw_l = fma(di, s_il, Qw_l);
+                            Qw_l = fma(di, S[i * 32 + lane], Qw_l);
+                            todo &= ~((2u << i) - 1u);                    // coordinates up to i have had their turn
+                            if (!todo) break;
+                            dc = candidate();
                         }
                     }
                     const double w_new_l = w_l + delta_l;
                     nz = __ballot_sync(0xffffffffu, delta_l != 0.0);
+                    if (lane == 0) pmv[m * NBLK + b] = (unsigned char)__popc(nz);
                     if (ok_l) {
                         dwmax_l = fmax(dwmax_l, fabs(delta_l));
                         wmax_l = fmax(wmax_l, fabs(w_new_l));

@@ -138,6 +138,7 @@ enet_cd_gram_kernel(const double *const *__restrict__ prob_Q, const double *cons
     unsigned *act = reinterpret_cast<unsigned *>(dlt + 32);       // [NBLK] active-coordinate masks
     unsigned *drp = act + NBLK;                       // [NBLK] screened-out coordinates with w != 0
     unsigned *ctl = drp + NBLK;                       // [0] rows moved in the current block, [1] done
+    unsigned char *pmv = reinterpret_cast<unsigned char *>(ctl + 2);     // [NBLK] coordinates moved in the last sweep
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int mdl = blockIdx.x;
@@ -161,6 +162,7 @@ enet_cd_gram_kernel(const double *const *__restrict__ prob_Q, const double *cons
         const int rem = C - (b << 5);
         act[b] = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
         drp[b] = 0u;
+        pmv[b] = 0;
     }
     __syncthreads();
 
@@ -308,17 +310,43 @@ enet_cd_gram_kernel(const double *const *__restrict__ prob_Q, const double *cons
                 const double a_l = fma(w_l, d_l, q_l);
                 const double k_pos = fma(-l1, inv_l, -w_l), k_neg = fma(l1, inv_l, -w_l);
                 double delta_l = 0.0;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    if (!((mask >> i) & 1u)) continue;                    // uniform: coordinate screened out
-                    const double s_il = inb ? S[i * 32 + lane] : 0.0;
+                // Every lane's candidate step from the CURRENT state, all 32 at once.  Until some coordinate
+                // moves the state does not change, so the lanes whose candidate is zero need no turn: the
+                // sweep jumps to the first lane (in coordinate order) whose candidate is non-zero, applies it
+                // exactly as the sequential algorithm would, and re-evaluates the lanes after it.  A sparse
+                // model pays for the coordinates that move, not for 32 serial steps per block.
+                auto candidate = [&]() -> double {
                     const double r = a_l - Qw_l;
                     const double dpos = fma(r, inv_l, k_pos), dneg = fma(r, inv_l, k_neg);
-                    double dc = (r > l1) ? dpos : ((r < -l1) ? dneg : -w_l);
-                    dc = ok_l ? dc : 0.0;
-                    const double di = __shfl_sync(0xffffffffu, dc, i);
-                    if (lane == i) delta_l = dc;
-                    Qw_l = fma(di, s_il, Qw_l);
+                    const double dc = (r > l1) ? dpos : ((r < -l1) ? dneg : -w_l);
+                    return ok_l ? dc : 0.0;
+                };
+                if (pmv[b] >= 20) {
+                    // dense block (20+ coordinates moved in the last sweep): the straight 32-step chain, no
+                    // vote on the dependent path
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        if (!((mask >> i) & 1u)) continue;                // uniform: coordinate screened out
+                        const double s_il = inb ? S[i * 32 + lane] : 0.0;
+                        const double dc = candidate();
+                        const double di = __shfl_sync(0xffffffffu, dc, i);
+                        if (lane == i) delta_l = dc;
+                        Qw_l = fma(di, s_il, Qw_l);
+                    }
+                } else {
+                    double dc = candidate();
+                    unsigned todo = mask;
+                    while (true) {
+                        const unsigned mv = __ballot_sync(0xffffffffu, dc != 0.0) & todo;
+                        if (!mv) break;
+                        const int i = __ffs(mv) - 1;
+                        const double di = __shfl_sync(0xffffffffu, dc, i);
+                        if (lane == i) delta_l = dc;
+                        Qw_l = fma(di, inb ? S[i * 32 + lane] : 0.0, Qw_l);
+                        todo &= ~((2u << i) - 1u);                        // coordinates up to i have had their turn
+                        if (!todo) break;
+                        dc = candidate();
+                    }
                 }
                 const double w_new_l = w_l + delta_l;
                 const unsigned nz = __ballot_sync(0xffffffffu, delta_l != 0.0);
@@ -328,7 +356,7 @@ enet_cd_gram_kernel(const double *const *__restrict__ prob_Q, const double *cons
                 }
                 if (delta_l != 0.0) w[j_l] = w_new_l;
                 dlt[lane] = delta_l;
-                if (lane == 0) ctl[0] = nz;
+                if (lane == 0) { ctl[0] = nz; pmv[b] = (unsigned char)__popc(nz); }
                 n_upd += __popc(nz);
                 ++n_blk;
                 int bn = b + 1;
@@ -925,7 +953,7 @@ extern "C" int sglm_center_stats_f64(const double *A_plus, const double *A_minus
 
 static size_t cd_smem_bytes(int C) {
     const int Cp = (C + 1) & ~1, nblk = (C + 31) / 32;
-    return (size_t)(2 * Cp + 2 * 1024 + 128 + 32) * sizeof(double) + (size_t)(2 * nblk + 2) * sizeof(unsigned) + 64;
+    return (size_t)(2 * Cp + 2 * 1024 + 128 + 32) * sizeof(double) + (size_t)(2 * nblk + 2) * sizeof(unsigned) + (size_t)nblk + 64;
 }
 
 extern "C" int sglm_enet_cd_gram_f64(const double *const *prob_Q, const double *const *prob_q,
