@@ -258,6 +258,35 @@ def test_tensor_core_gram_cell_decomposition_is_exact():
         assert np.max(np.abs(got - want)) <= 1e-12 * np.max(np.abs(want))
 
 
+def test_cv_grid_kfold_partition_through_cells_matches_weighted_fp64_path():
+    """A K-fold PARTITION (disjoint test folds that cover every row): the cells of the tensor-core Gram are the
+    folds themselves and the full-data statistics are their sum — same CV results as the weighted fp64 DMMA path."""
+    import os
+    rng = np.random.default_rng(12)
+    T, C = 4000, 90
+    X = _mixed_design(T, C, 9)
+    y = X[:, :8].sum(1) + rng.standard_normal(T)
+    perm = rng.permutation(T)
+    cv_idx = [(np.sort(np.setdiff1d(perm, perm[k::4])), np.sort(perm[k::4])) for k in range(4)]
+    grid = [dict(alpha=a, l1_ratio=l, max_iter=1000, fit_intercept=True) for a in (0.0, 0.01, 1.0) for l in (0.0, 0.5)]
+    out = {}
+    for mode in ("dmma", "tc"):
+        os.environ["SGLM_GRAM"] = mode
+        try:
+            out[mode] = sglm_cv.cv_glm_mult_params(X, y, cv_idx, "Gaussian", [dict(g) for g in grid], score_method="r2")
+        finally:
+            os.environ.pop("SGLM_GRAM", None)
+        if mode == "tc":
+            assert nat.last_tc_plan["cells"] and nat.last_tc_plan["row_lists"] == 4
+            assert nat.last_tc_plan["n_pos"] <= T + 4 * 128
+    assert out["tc"]["best_params"] == out["dmma"]["best_params"]
+    for a, b in zip(out["tc"]["full_cv_results"], out["dmma"]["full_cv_results"]):
+        assert coef_rel_err(a["cv_coefs"], b["cv_coefs"]) < 1e-9
+        assert np.allclose(a["cv_scores_test"], b["cv_scores_test"], atol=1e-9)
+        assert abs(a["cv_R2_score"] - b["cv_R2_score"]) < 1e-9
+        assert coef_rel_err(a["model"].coef_, b["model"].coef_) < 1e-9
+
+
 def test_tensor_core_gram_rejects_nan():
     X = np.random.default_rng(0).standard_normal((300, 8))
     X[17, 3] = np.inf
