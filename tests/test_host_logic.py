@@ -165,6 +165,8 @@ def test_cd_launch_plan_parsing():
         assert eng._cd_plan(96, 10) == [(0, 10, 4, 1)]           # 3 coordinate blocks cannot feed 8 CTAs
         eng.CD_PLAN = None
         assert eng._cd_plan(410, 1500) == [(0, 1500, 0, 0)]       # narrow design: one CTA per model
+        assert eng._cd_plan(410, 1) == [(0, 1, 1, 4)]             # a single fit: one 4-CTA cluster
+        assert eng._cd_plan(100, 1) == [(0, 1, 0, 0)]
         assert eng._cd_plan(2000, 1500)[0][2:] == (4, 2)
         eng.CD_PLAN = "4x2"
         assert eng._cd_plan(6000, 100) == [(0, 100, 4, 4)]       # slice of 3000 columns x 4 models does not fit: wider cluster
