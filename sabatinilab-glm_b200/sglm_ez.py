@@ -75,10 +75,11 @@ def diff_cols(X, cols, append_to_base=True):
     return sglm_pp.diff(X, sglm_pp.get_column_nums(X, cols), append_to_base=append_to_base)
 
 
-def cv_idx_by_timeframe(X, y=None, timesteps_per_bucket=20, num_folds=10, test_size=None):
-    """GroupShuffleSplit over time buckets (backend/sglm_ez.py:193-217)."""
+def cv_idx_by_timeframe(X, y=None, timesteps_per_bucket=20, num_folds=10, test_size=None, device=None):
+    """GroupShuffleSplit over time buckets (backend/sglm_ez.py:193-217).  device="cuda": the same splits as
+    CUDA index tensors (see sglm_pp.cv_idx_from_bucket_ids)."""
     bucket_ids = sglm_pp.bucket_ids_by_timeframe(X.shape[0], timesteps_per_bucket=timesteps_per_bucket)
-    return sglm_pp.cv_idx_from_bucket_ids(bucket_ids, X, y=y, num_folds=num_folds, test_size=test_size)
+    return sglm_pp.cv_idx_from_bucket_ids(bucket_ids, X, y=y, num_folds=num_folds, test_size=test_size, device=device)
 
 
 def _bucket_codes(X, id_cols):
@@ -89,11 +90,12 @@ def _bucket_codes(X, id_cols):
     return ids.astype("category").cat.codes
 
 
-def cv_idx_by_trial_id(X, y=None, trial_id_columns=[], num_folds=5, test_size=None):
-    """GroupShuffleSplit keeping trials together (backend/sglm_ez.py:311-343)."""
+def cv_idx_by_trial_id(X, y=None, trial_id_columns=[], num_folds=5, test_size=None, device=None):
+    """GroupShuffleSplit keeping trials together (backend/sglm_ez.py:311-343).  device="cuda": the same splits as
+    CUDA index tensors."""
     X = pd.DataFrame(X)
-    return sglm_pp.cv_idx_from_bucket_ids(_bucket_codes(X, trial_id_columns), X, y=y, num_folds=num_folds,
-                                          test_size=test_size)
+    return sglm_pp.cv_idx_from_bucket_ids(np.asarray(_bucket_codes(X, trial_id_columns)), X, y=y, num_folds=num_folds,
+                                          test_size=test_size, device=device)
 
 
 def holdout_split_by_trial_id(X, y=None, id_cols=['nTrial', 'iBlock'], strat_col=None, strat_mode=None,

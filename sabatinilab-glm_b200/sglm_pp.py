@@ -296,16 +296,40 @@ def bucket_ids_by_timeframe(total_timesteps, timesteps_per_bucket=20):
     return np.arange(total_timesteps) // num_buckets
 
 
-def cv_idx_from_bucket_ids(bucket_ids, X, y=None, num_folds=None, test_size=None):
+def cv_idx_from_bucket_ids(bucket_ids, X, y=None, num_folds=None, test_size=None, device=None):
     """GroupShuffleSplit over the bucket ids (backend/sglm_pp.py:236-264); global numpy RNG
-    state decides the split, as in the reference."""
+    state decides the split, as in the reference.
+
+    device="cuda" (extension): the same splits as CUDA int64 index tensors.  The
+    group-level shuffle — the only random part — runs on the host exactly as scikit-learn's
+    GroupShuffleSplit does it (ShuffleSplit over the sorted unique groups, same draws from the global
+    numpy RNG); the expansion to the (millions of) row indices happens on the device, so the index
+    lists never cross the PCIe bus and `cv_glm_*` takes them as they are."""
     from sklearn.model_selection import GroupShuffleSplit
     if num_folds is None:
         num_folds = bucket_ids.max() + 1
     if test_size is None:
         test_size = 1 / num_folds
-    splitter = GroupShuffleSplit(n_splits=num_folds, test_size=test_size)
-    return list(splitter.split(X, y, bucket_ids))
+    if device is None:
+        splitter = GroupShuffleSplit(n_splits=num_folds, test_size=test_size)
+        return list(splitter.split(X, y, bucket_ids))
+    import torch
+    from sklearn.model_selection import ShuffleSplit
+    ids = bucket_ids if type(bucket_ids).__module__.startswith("torch") else torch.from_numpy(np.array(bucket_ids, copy=True))
+    ids = ids.to(device)
+    classes, inverse = torch.unique(ids, sorted=True, return_inverse=True)
+    n_classes = int(classes.numel())
+    out = []
+    # sklearn/model_selection/_split.py: GroupShuffleSplit._iter_indices = ShuffleSplit._iter_indices over the classes
+    for g_train, g_test in ShuffleSplit(n_splits=int(num_folds), test_size=test_size).split(np.empty((n_classes, 1))):
+        lut = torch.zeros(n_classes, dtype=torch.bool, device=ids.device)
+        lut[torch.from_numpy(g_test).to(ids.device)] = True
+        in_test = lut[inverse]
+        lut.zero_()
+        lut[torch.from_numpy(g_train).to(ids.device)] = True
+        in_train = lut[inverse]
+        out.append((torch.nonzero(in_train).reshape(-1), torch.nonzero(in_test).reshape(-1)))
+    return out
 
 
 def min_max_scale(X, lower_bound, upper_bound):

@@ -287,6 +287,37 @@ def test_cv_grid_kfold_partition_through_cells_matches_weighted_fp64_path():
         assert coef_rel_err(a["model"].coef_, b["model"].coef_) < 1e-9
 
 
+def test_device_side_fold_indices_equal_the_host_split():
+    """cv_idx_by_timeframe / cv_idx_by_trial_id with device="cuda" return the SAME splits as the
+    reference path (same draws from the global numpy RNG), as CUDA index tensors that cv_glm_* takes directly."""
+    T = 5000
+    X = pd.DataFrame({"a": np.arange(T, dtype=float), "nTrial": np.arange(T) // 37, "iBlock": np.arange(T) // 900})
+    for maker in (lambda dev: sglm_ez.cv_idx_by_timeframe(X, timesteps_per_bucket=20, num_folds=4, test_size=0.25, device=dev),
+                  lambda dev: sglm_ez.cv_idx_by_trial_id(X, trial_id_columns=["nTrial", "iBlock"], num_folds=3, test_size=0.2, device=dev)):
+        np.random.seed(7)
+        host = maker(None)
+        after_host = np.random.get_state()[1].copy()
+        np.random.seed(7)
+        dev = maker("cuda")
+        assert np.array_equal(after_host, np.random.get_state()[1])             # same RNG consumption
+        assert len(host) == len(dev)
+        for (tr_h, te_h), (tr_d, te_d) in zip(host, dev):
+            assert tr_d.is_cuda and tr_d.dtype == torch.int64
+            assert np.array_equal(tr_h, tr_d.cpu().numpy()) and np.array_equal(te_h, te_d.cpu().numpy())
+    # ... and a CV call on them
+    rng = np.random.default_rng(0)
+    Xd = rng.standard_normal((T, 6))
+    y = Xd[:, 0] + 0.1 * rng.standard_normal(T)
+    np.random.seed(3)
+    cv_dev = sglm_ez.cv_idx_by_timeframe(Xd, timesteps_per_bucket=50, num_folds=3, test_size=0.3, device="cuda")
+    np.random.seed(3)
+    cv_host = sglm_ez.cv_idx_by_timeframe(Xd, timesteps_per_bucket=50, num_folds=3, test_size=0.3)
+    grid = [dict(alpha=0.01, l1_ratio=0.5, max_iter=1000, fit_intercept=True)]
+    a = sglm_cv.cv_glm_mult_params(Xd, y, cv_dev, "Gaussian", [dict(g) for g in grid], score_method="r2")
+    b = sglm_cv.cv_glm_mult_params(Xd, y, cv_host, "Gaussian", [dict(g) for g in grid], score_method="r2")
+    assert np.array_equal(a["full_cv_results"][0]["cv_coefs"], b["full_cv_results"][0]["cv_coefs"])
+
+
 def test_tensor_core_gram_rejects_nan():
     X = np.random.default_rng(0).standard_normal((300, 8))
     X[17, 3] = np.inf
