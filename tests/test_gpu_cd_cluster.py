@@ -124,3 +124,26 @@ def test_wide_design_default_plan_matches_first_generation():
     W1, i1, _ = _solve(models, C, None)
     assert np.array_equal(W0, W1)
     assert np.array_equal(i0[:, 2:4], i1[:, 2:4])
+
+
+def test_random_shapes_and_widths_against_the_first_generation_kernel():
+    """Seeded sweep over design widths that are not multiples of 32 (odd widths, one or two blocks per CTA,
+    a ragged last block), ragged groups and random launch plans."""
+    rng = np.random.default_rng(2024)
+    for case in range(8):
+        C = int(rng.integers(40, 700))
+        n_sets = int(rng.integers(1, 4))
+        probs, _, _ = _problems(int(rng.integers(C + 200, 2500)), C, n_sets, seed=500 + case,
+                                zero_col=int(rng.integers(0, C)) if case % 2 else None)
+        n_models = int(rng.integers(1, 14))
+        models = [eng.ModelSpec(probs[int(rng.integers(0, n_sets))], "enet", float(10 ** rng.uniform(-3.5, 0.5)),
+                                float(rng.choice([0.05, 0.5, 1.0])), int(rng.choice([3, 1000])), float(rng.choice([1e-4, 1e-7])))
+                  for _ in range(n_models)]
+        W0, i0, s0 = _solve(models, C, "0x0")
+        shapes = list(rng.choice(SHAPES, size=3, replace=False))
+        plans = shapes + [f"{shapes[0]}@0.4,{shapes[1]}", f"{shapes[2]}@0.5,0x0"]
+        for plan in plans:
+            W1, i1, s1 = _solve(models, C, plan)
+            assert np.array_equal(W0, W1), (case, C, plan)
+            assert np.array_equal(i0[:, 2:4], i1[:, 2:4]), (case, C, plan)
+            assert np.array_equal(s0, s1), (case, C, plan)
