@@ -174,8 +174,16 @@ tc_slice_kernel(const double *__restrict__ X, long long ldx, const double *__res
         const int S = colS[c], E = colE[c];
         const double2 v01 = *reinterpret_cast<const double2 *>(&tile[cc][4 * pq]);
         const double2 v23 = *reinterpret_cast<const double2 *>(&tile[cc][4 * pq + 2]);
-        double r0 = scalbn(v01.x, -E) * 64.0, r1 = scalbn(v01.y, -E) * 64.0;
-        double r2 = scalbn(v23.x, -E) * 64.0, r3 = scalbn(v23.y, -E) * 64.0;
+        double r0, r1, r2, r3;
+        if (E > -900 && E < 900) {
+            // scaling by 2^(6-E) as ONE exact multiplication by a power of two built from its exponent bits
+            // (scalbn is a multi-instruction routine; this pass was issue-bound: profiles/r1_cd_cluster.txt §14)
+            const double sc = __longlong_as_double((long long)(1023 + 6 - E) << 52);
+            r0 = v01.x * sc; r1 = v01.y * sc; r2 = v23.x * sc; r3 = v23.y * sc;
+        } else {
+            r0 = scalbn(v01.x, -E) * 64.0; r1 = scalbn(v01.y, -E) * 64.0;
+            r2 = scalbn(v23.x, -E) * 64.0; r3 = scalbn(v23.y, -E) * 64.0;
+        }
         for (int k = 1; k <= S; ++k) {
             const double d0 = rint(r0), d1 = rint(r1), d2 = rint(r2), d3 = rint(r3);
             r0 = (r0 - d0) * 128.0; r1 = (r1 - d1) * 128.0; r2 = (r2 - d2) * 128.0; r3 = (r3 - d3) * 128.0;
