@@ -176,3 +176,15 @@ def test_cd_launch_plan_parsing():
             eng._cd_plan(2000, 10)
     finally:
         eng.CD_PLAN, eng.CD_GROUP, eng.CD_CLUSTER = old
+
+
+def test_union_of_overlapping_call_intervals():
+    """bench.py times the coordinate-descent grid as the union of its concurrent launches."""
+    old = nat.last_intervals
+    try:
+        nat.last_intervals = [("a", 0.0, 10.0), ("b", 5.0, 12.0), ("a", 20.0, 21.0), ("c", 0.0, 100.0)]
+        assert nat.union_ms(("a", "b")) == pytest.approx(13.0)
+        assert nat.union_ms(("a",)) == pytest.approx(11.0)
+        assert nat.union_ms(("zzz",)) == 0.0
+    finally:
+        nat.last_intervals = old
