@@ -71,6 +71,31 @@ int sglm_timeshift_f64_ranged(const double *X, int64_t T, int32_t n_cols_in, int
 int sglm_crop_rows_f64(const double *X, int64_t ldx, int64_t row_begin, int64_t n_rows,
                        int32_t n_cols, double *out, int64_t ldo, void *stream);
 
+/* Fused dropna (the `dropna()` every driver applies between the lag builder and the fit,
+ * er_refactored_from_scratch_cleanup.py:427-429; backend/test/test_sglm_ez.py:28):
+ *   lag_valid_rows : valid[t] = 1 when row t of the lag design would hold no NaN — decided from the base
+ *                    signals and the column map, the design is not built.  fill_is_nan != 0: rows whose source
+ *                    row falls outside [0, T) are invalid (NaN padding).  summary3 (device int64[3]) =
+ *                    {valid rows, first valid row, last valid row}.
+ *   mask_compact_rows : ascending indices of the set rows of `valid` (rows must hold summary3[0] entries).
+ *   timeshift_rows : the gather restricted to listed rows, out[r, c] = X[rows[r] - col_shift[c], col_src[c]].
+ * When the valid rows are one contiguous range (no NaN in the base signals) the plain gather + a row view is used. */
+int sglm_lag_valid_rows(const double *X, int64_t T, int32_t n_cols_in, int64_t ldx, const int32_t *col_src,
+                        const int32_t *col_shift, int32_t n_cols_out, int32_t shift_min, int32_t shift_max,
+                        int32_t fill_is_nan, uint8_t *valid, int64_t *summary3, void *stream);
+/* Row mask of an index list (positions in [0, T); mask holds T rounded up to a multiple of 4 bytes, 4-byte
+ * aligned): mask[t] = 1 for listed rows, *dup_flag = 1 when a row is listed twice.  With mask_compact_rows this
+ * gives the sorted, duplicate-free test rows of a fold (backend/sglm_cv.py:106-110) without a sort. */
+int sglm_index_mask_u8(const int64_t *idx, int64_t n_idx, uint8_t *mask, int64_t T, int32_t *dup_flag, void *stream);
+/* np.roll(y, shift) (the `roll` key of a parameter set, backend/sglm_cv.py:95-96): out[(i + shift) mod n] = y[i]. */
+int sglm_roll_f64(const double *y, int64_t n, int64_t shift, double *out, void *stream);
+size_t sglm_mask_compact_workspace_bytes(int64_t T);
+int sglm_mask_compact_rows(const uint8_t *valid, int64_t T, int64_t *rows, void *workspace,
+                           size_t workspace_bytes, void *stream);
+int sglm_timeshift_rows_f64(const double *X, int64_t T, int32_t n_cols_in, int64_t ldx, const int32_t *col_src,
+                            const int32_t *col_shift, int32_t n_cols_out, uint64_t fill_bits,
+                            const int64_t *rows, int64_t n_rows, double *out, int64_t ldo, void *stream);
+
 /* ------------------------------------------------------------------------- *
  * Sufficient statistics.  Replaces the X'X / X'y work that every sklearn fit
  * repeats per (fold, alpha) (sklearn/linear_model/_ridge.py:215-227,
@@ -201,6 +226,8 @@ int sglm_enet_cd_gram_f64(const double *const *prob_Q, const double *const *prob
  *   prob_tmap: device array (64-byte aligned) of one TMA descriptor per problem, encoded on the host by
  *   sglm_enet_cd_cluster_encode_tmaps (Q_dev_ptrs = the same device pointers as prob_Q, as host values)
  *   into n_prob * sglm_enet_cd_cluster_tmap_bytes() bytes and copied to the device by the caller.
+ *   group_stats (may be NULL): [n_groups][2] = {rows of Q the group's cluster loaded (a moved row is loaded once
+ *   for all models of the group: 8*C bytes each), coordinate-block records processed} — measurement only.
  * sglm_enet_cd_cluster_supported(group_size, cluster_size) -> 1 if that shape is compiled in. */
 int sglm_enet_cd_cluster_supported(int32_t group_size, int32_t cluster_size);
 size_t sglm_enet_cd_cluster_tmap_bytes(void);
@@ -213,7 +240,8 @@ int sglm_enet_cd_cluster_f64(const double *const *prob_Q, const double *const *p
                              const double *l1_reg, const double *l2_reg, const double *tol,
                              const int32_t *max_iter, int32_t n_groups, int32_t group_size,
                              int32_t cluster_size, int32_t warm_start, int32_t do_screening,
-                             double *W, int64_t ldw, double *info, const void *prob_tmap, void *stream);
+                             double *W, int64_t ldw, double *info, const void *prob_tmap,
+                             double *group_stats, void *stream);
 
 /* ------------------------------------------------------------------------- *
  * (a7, a8) batched Cholesky solve — Ridge / OLS.  Replaces sklearn
@@ -278,6 +306,18 @@ int sglm_poisson_irls_prepare_f64(const double *X, int64_t ldx, const double *y,
                                   int64_t T, int32_t C, const double *w, const double *b_dev,
                                   double *weight, double *z, double *sums, void *workspace,
                                   void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * Measurement probe (bench.py; no reference counterpart): reads `n_doubles` doubles
+ * `repeats` times with the access pattern of the coordinate-descent panel (16-byte
+ * loads, 8 in flight per thread).  A buffer that fits L2 measures the L2 -> SM read
+ * bandwidth, one far larger than L2 the HBM read bandwidth; the caller times it.
+ * ------------------------------------------------------------------------- */
+/* Issue rate of tcgen05.mma kind::i8 (operands resident in shared memory, one CTA per SM): int8 MACs issued =
+ * *n_ctas_host * iters * 8 * 128 * 256 * 32; the denominator of the Gram GEMM's tensor-pipe fraction. */
+int sglm_probe_mma_i8(int32_t iters, int64_t *n_ctas_host, void *stream);
+int sglm_probe_read_f64(const double *buf, int64_t n_doubles, int32_t repeats, int32_t ctas_per_sm,
+                        double *sink, void *stream);
 
 #ifdef __cplusplus
 }

@@ -34,7 +34,10 @@ def is_torch(x):
 
 
 def _values(x):
-    """DataFrame / Series -> ndarray (reference: X.values, backend/sglm_ez.py:376-377)."""
+    """DataFrame / Series -> ndarray (reference: X.values, backend/sglm_ez.py:376-377); a device-resident
+    design (sglm_pp.DeviceDesign) -> its CUDA tensor."""
+    if type(x).__name__ == "DeviceDesign":
+        return x.tensor()
     if hasattr(x, "values") and not is_torch(x) and not isinstance(x, np.ndarray):
         return x.values
     return x
@@ -80,6 +83,8 @@ def device_vector(y):
             t = t.to("cuda", non_blocking=True)
         return t.contiguous()
     a = np.ascontiguousarray(np.asarray(y).reshape(-1), dtype=np.float64)
+    if not a.flags.writeable:
+        a = a.copy()
     return torch.from_numpy(a).to("cuda")
 
 
@@ -143,6 +148,32 @@ def index_counts(idx, T):
     if it.numel():
         call("sglm_index_counts_f64", ptr(it), it.numel(), ptr(counts), T, stream_ptr())
     return counts
+
+
+def roll_vector(yd, shift):
+    """np.roll(y, shift) on the device (backend/sglm_cv.py:95-96)."""
+    out = _empty((yd.numel(),))
+    call("sglm_roll_f64", ptr(yd), yd.numel(), int(shift), ptr(out), stream_ptr())
+    return out
+
+
+def sorted_unique_rows(idx_t, T):
+    """Ascending, duplicate-free positions of an index list (CUDA int64, values in [0, T)) without a sort: a row
+    mask (duplicates detected while setting it) followed by an ordered compaction.  Returns a tensor SHORTER than
+    the input when the list repeats rows."""
+    torch = nat.require_cuda()
+    mask = torch.empty((T + 3) // 4 * 4 + 4, dtype=torch.uint8, device="cuda")
+    flags = torch.empty(4, dtype=torch.int64, device="cuda")            # [0] duplicate flag (int32 view)
+    call("sglm_index_mask_u8", ptr(idx_t), idx_t.numel(), ptr(mask), T, ptr(flags), stream_ptr())
+    dup = int(flags.view(torch.int32)[0].item())
+    n = int(idx_t.numel())
+    if dup:
+        return idx_t[:max(n - 1, 0)]
+    rows = torch.empty(n, dtype=torch.int64, device="cuda")
+    wb = nat.lib().sglm_mask_compact_workspace_bytes(T)
+    ws = torch.empty((wb + 7) // 8, dtype=torch.int64, device="cuda")
+    call("sglm_mask_compact_rows", ptr(mask), T, ptr(rows), ptr(ws), ws.numel() * 8, stream_ptr())
+    return rows
 
 
 def suffstats(Xd, Yd, W=None, rows_hint=None):
@@ -338,6 +369,25 @@ CD_GROUP, CD_CLUSTER = None, None     # override of (models per cluster, CTAs pe
 
 
 CD_PLAN = None      # override of the launch plan, e.g. "4x2@0.2,4x1" (see _cd_plan)
+CD_COLLECT_STATS = False   # bench.py: keep per-part device statistics of the coordinate-descent launches
+cd_parts_log = []          # [{shape (M, K), slots (r0, r1), group_stats [n_groups, 2] | None, info [n_slots, 6]}]
+
+
+def cd_stats():
+    """Summary of the logged coordinate-descent parts (synchronises): rows of Q loaded through L2 (a moved row
+    once per cluster group; once per model in the per-model kernel), coordinate updates, the longest chain of
+    coordinate blocks one model walked.  Clears the log."""
+    out = []
+    for part in cd_parts_log:
+        r0, r1 = part["slots"]
+        info = part["info"][r0:r1].cpu().numpy()
+        rows = float(part["group_stats"][:, 0].sum().item()) if part["group_stats"] is not None else float(info[:, 3].sum())
+        out.append(dict(shape="%dx%d" % part["shape"], models=r1 - r0, row_updates=float(info[:, 3].sum()),
+                        rows_loaded=rows, max_blocks_one_model=float(info[:, 4].max()) if r1 > r0 else 0.0,
+                        max_sweeps=float(info[:, 2].max()) if r1 > r0 else 0.0,
+                        register_phase_share_heaviest=float(info[int(np.argmax(info[:, 4])), 5]) if r1 > r0 else 0.0))
+    cd_parts_log.clear()
+    return out
 _SIDE_STREAMS = {}
 
 
@@ -518,12 +568,17 @@ def solve_models(models, C, do_screening=True):
                         groups.sort(key=lambda g: g[0])
                         gp = _dev(np.array([g[1] for g in groups], dtype=np.int32), np.int32)
                         gs = _dev(np.array([g[2] for g in groups], dtype=np.int32).reshape(-1), np.int32)
+                        gst = _zeros((len(groups), 2)) if CD_COLLECT_STATS else None
                         keep += [gp, gs]
+                        if gst is not None:
+                            cd_parts_log.append(dict(shape=(gsz, csz), slots=(r0, r1), group_stats=gst, info=info_d))
                         call("sglm_enet_cd_cluster_f64", ptr(Qp), ptr(qp), ptr(dp), ptr(yy), ldq, C, ptr(gp), ptr(gs),
                              ptr(pack_f[0]), ptr(pack_f[1]), ptr(pack_f[2]), ptr(pack_i[1]), len(groups), gsz, csz,
                              int(warm) | (int(CD_DEBUG_TIMER) << 8), int(do_screening), ptr(Wcd), ldw, ptr(info_d),
-                             ptr(tm_d), stream_ptr())
+                             ptr(tm_d), ptr(gst), stream_ptr())
                     else:
+                        if CD_COLLECT_STATS:
+                            cd_parts_log.append(dict(shape=(0, 0), slots=(r0, r1), group_stats=None, info=info_d))
                         call("sglm_enet_cd_gram_f64", ptr(Qp), ptr(qp), ptr(dp), ptr(yy), ldq, C, ptr(pack_i[0][r0:]),
                              ptr(pack_f[0][r0:]), ptr(pack_f[1][r0:]), ptr(pack_f[2][r0:]), ptr(pack_i[1][r0:]),
                              r1 - r0, int(warm), int(do_screening), ptr(Wcd[r0:]), ldw, ptr(info_d[r0:]), stream_ptr())

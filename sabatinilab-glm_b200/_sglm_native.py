@@ -23,6 +23,13 @@ _PROTOTYPES = {
     "sglm_timeshift_f64": (c_i32, [c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_i32, c_u64, c_vp, c_i64, c_vp]),
     "sglm_timeshift_f64_ranged": (c_i32, [c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_i32, c_i32, c_i32,
                                           c_u64, c_vp, c_i64, c_vp]),
+    "sglm_lag_valid_rows": (c_i32, [c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "sglm_index_mask_u8": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
+    "sglm_roll_f64": (c_i32, [c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "sglm_mask_compact_workspace_bytes": (c_sz, [c_i64]),
+    "sglm_mask_compact_rows": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
+    "sglm_timeshift_rows_f64": (c_i32, [c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_i32, c_u64, c_vp, c_i64, c_vp,
+                                        c_i64, c_vp]),
     "sglm_crop_rows_f64": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_i64, c_vp]),
     "sglm_suffstats_workspace_bytes": (c_sz, [c_i64, c_i32, c_i32, c_i32, c_vp]),
     "sglm_suffstats_f64": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_i64, c_i32,
@@ -48,7 +55,7 @@ _PROTOTYPES = {
                                       c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp]),
     "sglm_enet_cd_cluster_supported": (c_i32, [c_i32, c_i32]),
     "sglm_enet_cd_cluster_f64": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
-                                         c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp]),
+                                         c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "sglm_enet_cd_cluster_tmap_bytes": (c_sz, []),
     "sglm_enet_cd_cluster_smem_bytes": (c_sz, [c_i32, c_i32, c_i32]),
     "sglm_enet_cd_cluster_encode_tmaps": (c_i32, [c_vp, c_i32, c_i32, c_i64, c_vp]),
@@ -64,6 +71,8 @@ _PROTOTYPES = {
     "sglm_score_workspace_bytes": (c_sz, []),
     "sglm_score_f64": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp,
                                c_vp, c_vp]),
+    "sglm_probe_mma_i8": (c_i32, [c_i32, c_vp, c_vp]),
+    "sglm_probe_read_f64": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
     "sglm_poisson_irls_prepare_f64": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp,
                                               c_vp, c_vp, c_vp, c_vp]),
 }

@@ -65,7 +65,8 @@ extern "C" int sglm_enet_cd_cluster_f64(const double *const *prob_Q, const doubl
                                         const double *l1_reg, const double *l2_reg, const double *tol,
                                         const int32_t *max_iter, int32_t n_groups, int32_t group_size,
                                         int32_t cluster_size, int32_t warm_start, int32_t do_screening, double *W,
-                                        int64_t ldw, double *info, const void *prob_tmap, void *stream) {
+                                        int64_t ldw, double *info, const void *prob_tmap, double *group_stats,
+                                        void *stream) {
     SGLM_CHECK_ARG(C > 0 && n_groups >= 0 && ldq >= C && ldw >= C, SGLM_E_SHAPE, "enet_cd_cluster: bad shape");
     if (n_groups == 0) return SGLM_OK;
     SGLM_CHECK_ARG(prob_Q && prob_q && prob_diag && prob_yy && prob_of_group && model_of_slot && l1_reg && l2_reg &&
@@ -78,7 +79,7 @@ extern "C" int sglm_enet_cd_cluster_f64(const double *const *prob_Q, const doubl
                    "enet_cd_cluster: C=%d too small for a cluster of %d", C, cluster_size);
     cdc::Args a{prob_Q, prob_q, prob_diag, prob_yy, (long long)ldq, C, prob_of_group, model_of_slot, l1_reg, l2_reg,
                 tol, max_iter, n_groups, warm_start, do_screening, W, (long long)ldw, info,
-                (const CUtensorMap *)prob_tmap, (cudaStream_t)stream, 0};
+                (const CUtensorMap *)prob_tmap, (cudaStream_t)stream, 0, group_stats};
     if (const char *v = getenv("SGLM_CDC_VARIANT")) a.variant = atoi(v);      // tuning switch
     if (group_size == 1) return cdc::launch_m1(a, cluster_size);
     if (group_size == 2) return cdc::launch_m2(a, cluster_size);

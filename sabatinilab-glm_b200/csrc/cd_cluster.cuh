@@ -192,7 +192,7 @@ enet_cd_cluster_kernel(const double *const *__restrict__ prob_Q, const double *c
                        const double *__restrict__ l2_reg, const double *__restrict__ tol_in,
                        const int *__restrict__ max_iter_in, int warm_start, int do_screening,
                        double *__restrict__ W, long long ldw, double *__restrict__ info,
-                       const CUtensorMap *__restrict__ tmaps) {
+                       const CUtensorMap *__restrict__ tmaps, double *__restrict__ group_stats) {
     constexpr int NT = (M + NB) * 32;
     constexpr int NTB = NB * 32;
     extern __shared__ __align__(128) unsigned char smraw[];
@@ -283,6 +283,7 @@ enet_cd_cluster_kernel(const double *const *__restrict__ prob_Q, const double *c
     warm_start &= 1;
     const long long t_begin = clock64();
     unsigned rc = 0u;             // records published so far (identical in every thread of the cluster)
+    long long rows_loaded = 0;    // panel warps: rows of Q the records asked for (union over the M models)
     unsigned xpar = 0u;
     int sweep = 0;
 
@@ -641,6 +642,7 @@ enet_cd_cluster_kernel(const double *const *__restrict__ prob_Q, const double *c
                 unsigned mk[M], um = 0u;
 #pragma unroll
                 for (int mm = 0; mm < M; ++mm) { mk[mm] = (unsigned)rmask[slot * M + mm]; um |= mk[mm]; }
+                rows_loaded += __popc(um);          // rows of Q this record makes the cluster load (once for the M models)
                 if (um) {
                     const double2 *Q2 = reinterpret_cast<const double2 *>(Q + (long long)(b << 5) * ldq + col0);
                     // A model that moved sent all 32 deltas (exact zeros for the rows that stayed), a model that
@@ -712,6 +714,10 @@ enet_cd_cluster_kernel(const double *const *__restrict__ prob_Q, const double *c
         }
     }
     cluster_sync_all();
+    if (group_stats && rank == 0 && !is_seq && bt == 0) {
+        group_stats[2 * grp + 0] = (double)rows_loaded;      // each row = 8*C bytes through the cluster's L2 ports
+        group_stats[2 * grp + 1] = (double)rc;               // records (coordinate blocks) processed
+    }
     if (rank == 0 && is_seq && valid && lane == 0) {
         double su = 0.0, sb = 0.0, st = 0.0;
         for (int k = 0; k < K; ++k) {
@@ -732,7 +738,7 @@ static int launch(const double *const *prob_Q, const double *const *prob_q, cons
                   const double *prob_yy, long long ldq, int C, const int *prob_of_group, const int *model_of_slot,
                   const double *l1_reg, const double *l2_reg, const double *tol, const int *max_iter, int n_groups,
                   int warm_start, int do_screening, double *W, long long ldw, double *info, const CUtensorMap *tmaps,
-                  cudaStream_t st) {
+                  double *group_stats, cudaStream_t st) {
     const Layout L = make_layout(M, K, NB, C);
     SGLM_CHECK_ARG(L.total <= 227 * 1024, SGLM_E_UNSUPPORTED,
                    "enet_cd_cluster: C=%d needs %zu bytes of shared memory per CTA (> 227 KB)", C, L.total);
@@ -753,7 +759,7 @@ static int launch(const double *const *prob_Q, const double *const *prob_q, cons
     cfg.numAttrs = 1;
     SGLM_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, prob_Q, prob_q, prob_diag, prob_yy, ldq, C, prob_of_group,
                                     model_of_slot, l1_reg, l2_reg, tol, max_iter, warm_start, do_screening, W, ldw,
-                                    info, tmaps));
+                                    info, tmaps, group_stats));
     return SGLM_OK;
 }
 
@@ -765,13 +771,14 @@ struct Args {
     const double *prob_yy; long long ldq; int C; const int *prob_of_group; const int *model_of_slot;
     const double *l1_reg; const double *l2_reg; const double *tol; const int *max_iter; int n_groups;
     int warm_start; int do_screening; double *W; long long ldw; double *info; const CUtensorMap *tmaps; cudaStream_t st; int variant;
+    double *group_stats;
 };
 
 template <int M, int K, int NB, int CH, int RG, int MINB>
 static int launch_a(const Args &a) {
     return launch<M, K, NB, CH, RG, MINB>(a.prob_Q, a.prob_q, a.prob_diag, a.prob_yy, a.ldq, a.C, a.prob_of_group,
                                     a.model_of_slot, a.l1_reg, a.l2_reg, a.tol, a.max_iter, a.n_groups,
-                                    a.warm_start, a.do_screening, a.W, a.ldw, a.info, a.tmaps, a.st);
+                                    a.warm_start, a.do_screening, a.W, a.ldw, a.info, a.tmaps, a.group_stats, a.st);
 }
 
 // Panel shapes (panel warps NB, 16-byte chunks per thread CH, rows per load group RG, min CTAs per SM).

@@ -419,6 +419,50 @@ tc_gram_i8_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restri
     }
 }
 
+// Measurement probe: the issue rate of tcgen05.mma kind::i8 with both operands resident in shared memory (no
+// loads in the loop) — the denominator the Gram GEMM's tensor-pipe fraction is quoted against.  One CTA per SM,
+// `iters` x (4 K-steps x 2 accumulators) UMMAs of M=128, N=256, K=32 on one stage of (arbitrary) operand bytes.
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_mma_probe_kernel(int iters) {
+    extern __shared__ __align__(1024) uint8_t tc_smem[];
+    uint8_t *base = (uint8_t *)(((uintptr_t)tc_smem + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = (uint64_t *)(base + TC_STAGE_BYTES);
+    uint32_t *tmem_slot = (uint32_t *)(bars + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < (int)(TC_STAGE_BYTES / 4); i += TC_THREADS) ((uint32_t *)base)[i] = 0x01010101u * (i & 3);
+    if (threadIdx.x == 0) { mbar_init(bars, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot;
+    if (warp == 1 && lane == 0) {
+        constexpr uint32_t idesc = tc_idesc_i8();
+        const uint64_t da0 = umma_desc_k_sw128(smem_u32(base));
+        const uint64_t da1 = umma_desc_k_sw128(smem_u32(base + 128 * TC_BK));
+        const uint64_t db = umma_desc_k_sw128(smem_u32(base + TC_BM * TC_BK));
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int k = 0; k < TC_BK / 32; ++k) {
+                tc_mma_i8(tmem_acc, da0 + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) ? 1u : 0u);
+                tc_mma_i8(tmem_acc + 256u, da1 + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) ? 1u : 0u);
+            }
+        }
+        tc_commit(bars);
+        mbar_wait(bars, 0);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(512));
+    }
+}
+
 // Plain-CUDA-core version of the same tile computation (validation of the tcgen05 path on the
 // GPU itself: the integer results must be identical).  One thread per output element.
 __global__ void __launch_bounds__(256)
@@ -693,6 +737,18 @@ extern "C" int sglm_gram_tc_analyze_scaled_f64(const double *X, int64_t ldx, con
                                                uint64_t *colmax_scratch, int32_t *flag, void *stream) {
     SGLM_CHECK_ARG(max_planes >= 1 && max_planes <= TC_SMAX, SGLM_E_INVALID_ARG, "gram_tc_analyze_scaled: max_planes out of range");
     return gram_tc_analyze(X, ldx, Y, ldy, n_y, T, C, row_scale, max_planes, colE, colS, colmax_scratch, flag, stream);
+}
+
+// int8 MACs issued = n_ctas * iters * 8 UMMAs * (128 * 256 * 32); the caller times the call with CUDA events.
+extern "C" int sglm_probe_mma_i8(int32_t iters, int64_t *n_ctas_host, void *stream) {
+    SGLM_CHECK_ARG(iters >= 1 && n_ctas_host, SGLM_E_INVALID_ARG, "probe_mma_i8: bad argument");
+    const size_t smem = 1024 + (size_t)TC_STAGE_BYTES + 256;
+    SGLM_CUDA_OK(cudaFuncSetAttribute(tc_mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int n = sm_count();
+    *n_ctas_host = n;
+    tc_mma_probe_kernel<<<n, TC_THREADS, smem, (cudaStream_t)stream>>>(iters);
+    SGLM_LAUNCH_OK("tc_mma_probe_kernel");
+    return SGLM_OK;
 }
 
 extern "C" size_t sglm_gram_tc_workspace_bytes(int32_t n_aug, const int32_t *colS_host, int32_t n_sets,

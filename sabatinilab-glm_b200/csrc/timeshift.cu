@@ -120,6 +120,153 @@ crop_rows_kernel(const double *__restrict__ X, long long ldx, long long row_begi
     }
 }
 
+// Gather restricted to listed rows (fused dropna compaction, er_refactored_from_scratch_cleanup.py:427-429:
+// the rows pandas' dropna would remove are never built): out[r, c] = X[rows[r] - shift_c, src_c] or fill.
+// Consecutive r mostly list consecutive rows, so a warp's source reads stay within a few cache lines (L2 / L1).
+__global__ void __launch_bounds__(TS_THREADS)
+timeshift_rows_kernel(const uint64_t *__restrict__ X, long long T, long long ldx,
+                      const int *__restrict__ col_src, const int *__restrict__ col_shift, int C,
+                      uint64_t fill, const long long *__restrict__ rows, long long n_rows,
+                      uint64_t *__restrict__ out, long long ldo) {
+    const long long total = n_rows * (long long)C;
+    for (long long e = (long long)blockIdx.x * TS_THREADS + threadIdx.x; e < total;
+         e += (long long)gridDim.x * TS_THREADS) {
+        const long long r = e / C;
+        const int c = (int)(e - r * C);
+        const long long ts = rows[r] - col_shift[c];
+        __stcs(out + r * ldo + c, (ts >= 0 && ts < T) ? X[ts * ldx + col_src[c]] : fill);
+    }
+}
+
+// Rows of the lag design that hold no NaN, decided from the BASE signals and the column map (the design itself
+// is not needed): row t is dropped when a source row t - shift_c falls outside [0, T) and the fill is NaN, or when
+// X[t - shift_c, src_c] is NaN for some column c.  Pass 1 marks the edge rows, pass 2 scans the T x P base signals
+// once and scatters every NaN it finds to the (few) design rows it reaches.
+__global__ void __launch_bounds__(256)
+lag_valid_init_kernel(unsigned char *__restrict__ valid, long long T, int smin, int smax, int fill_is_nan) {
+    for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < T; t += (long long)gridDim.x * 256)
+        valid[t] = (!fill_is_nan || (t >= (long long)smax && t < T + (long long)smin)) ? 1 : 0;
+}
+__global__ void __launch_bounds__(256)
+lag_valid_scatter_kernel(const double *__restrict__ X, long long T, int P, long long ldx,
+                         const int *__restrict__ col_src, const int *__restrict__ col_shift, int C,
+                         unsigned char *__restrict__ valid) {
+    const long long total = T * (long long)P;
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+        const long long u = e / P;
+        const int p = (int)(e - u * P);
+        const double v = X[u * ldx + p];
+        if (v == v) continue;
+        for (int c = 0; c < C; ++c)
+            if (col_src[c] == p) {
+                const long long t = u + col_shift[c];
+                if (t >= 0 && t < T) valid[t] = 0;
+            }
+    }
+}
+// summary of a 0/1 row mask: out3 = {count, first set row, last set row} (first = T, last = -1 when empty)
+__global__ void __launch_bounds__(256)
+mask_summary_kernel(const unsigned char *__restrict__ valid, long long T, long long *__restrict__ out3) {
+    long long cnt = 0, first = T, last = -1;
+    for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < T; t += (long long)gridDim.x * 256)
+        if (valid[t]) { ++cnt; first = min(first, t); last = max(last, t); }
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+        last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd((unsigned long long *)out3, (unsigned long long)cnt);
+        atomicMin(out3 + 1, first);
+        atomicMax(out3 + 2, last);
+    }
+}
+// Ordered compaction of the set rows of a mask: block b owns rows [b*CH, (b+1)*CH); pass A counts, a one-block
+// exclusive scan of the block counts follows, pass B writes the row indices in ascending order.
+constexpr int CMP_CH = 4096;
+__global__ void __launch_bounds__(256)
+mask_block_count_kernel(const unsigned char *__restrict__ valid, long long T, long long *__restrict__ counts) {
+    const long long t0 = (long long)blockIdx.x * CMP_CH;
+    int c = 0;
+    for (int i = threadIdx.x; i < CMP_CH; i += 256) c += (t0 + i < T && valid[t0 + i]) ? 1 : 0;
+    __shared__ int sh[8];
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) { int s = 0; for (int w = 0; w < 8; ++w) s += sh[w]; counts[blockIdx.x] = s; }
+}
+__global__ void __launch_bounds__(1024)
+exclusive_scan_kernel(long long *__restrict__ counts, long long n) {
+    // one block; n = number of 4096-row blocks (T = 2M: 489)
+    __shared__ long long carry;
+    __shared__ long long buf[1024];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (long long base = 0; base < n; base += 1024) {
+        const long long i = base + threadIdx.x;
+        const long long v = i < n ? counts[i] : 0;
+        buf[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const long long add = threadIdx.x >= o ? buf[threadIdx.x - o] : 0;
+            __syncthreads();
+            buf[threadIdx.x] += add;
+            __syncthreads();
+        }
+        if (i < n) counts[i] = carry + buf[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += buf[1023];
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256)
+mask_compact_kernel(const unsigned char *__restrict__ valid, long long T, const long long *__restrict__ offs,
+                    long long *__restrict__ rows) {
+    // a warp owns 512 consecutive rows of the block's 4096 (ballot-ordered writes); warp prefix via shared memory
+    const long long t0 = (long long)blockIdx.x * CMP_CH;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ int wcnt[8];
+    unsigned m[16];
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const long long t = t0 + warp * 512 + k * 32 + lane;
+        m[k] = __ballot_sync(0xffffffffu, t < T && valid[t]);
+        c += __popc(m[k]);
+    }
+    if (lane == 0) wcnt[warp] = c;
+    __syncthreads();
+    long long pos = offs[blockIdx.x];
+    for (int w = 0; w < warp; ++w) pos += wcnt[w];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        if ((m[k] >> lane) & 1u) rows[pos + __popc(m[k] & ((1u << lane) - 1u))] = t0 + warp * 512 + k * 32 + lane;
+        pos += __popc(m[k]);
+    }
+}
+
+// Row mask of an index list (positions in [0, T)): mask[t] = 1 for listed rows; *dup is set when a row is listed
+// twice.  Bytes are set through 32-bit atomicOr on the containing word (mask must be 4-byte aligned, zeroed).
+__global__ void __launch_bounds__(256)
+index_mask_kernel(const long long *__restrict__ idx, long long n, unsigned *__restrict__ mask_words, long long T,
+                  int *__restrict__ dup) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const long long t = idx[i];
+        if (t < 0 || t >= T) continue;
+        const unsigned bit = 1u << ((t & 3) * 8);
+        if (atomicOr(mask_words + (t >> 2), bit) & bit) *dup = 1;
+    }
+}
+// np.roll(y, shift): out[(i + shift) mod n] = y[i]   (backend/sglm_cv.py:95-96)
+__global__ void __launch_bounds__(256)
+roll_kernel(const double *__restrict__ y, long long n, long long shift, double *__restrict__ out) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        long long j = i + shift;
+        if (j >= n) j -= n;
+        out[j] = y[i];
+    }
+}
+
 __global__ void minmax_shift_kernel(const int *__restrict__ col_shift, const int *__restrict__ col_src,
                                     int C, int n_cols_in, int *out4) {
     // out4 = {min shift, max shift, bad source flag, unused}
@@ -237,6 +384,101 @@ extern "C" int sglm_timeshift_f64(const double *X, int64_t T, int32_t n_cols_in,
     SGLM_CHECK_ARG(h4[2] == 0, SGLM_E_INVALID_ARG, "timeshift: col_src out of range");
     return sglm_timeshift_f64_ranged(X, T, n_cols_in, ldx, col_src, col_shift, n_cols_out, h4[0],
                                      h4[1], fill_bits, out, ldo, stream);
+}
+
+extern "C" int sglm_timeshift_rows_f64(const double *X, int64_t T, int32_t n_cols_in, int64_t ldx,
+                                      const int32_t *col_src, const int32_t *col_shift, int32_t n_cols_out,
+                                      uint64_t fill_bits, const int64_t *rows, int64_t n_rows, double *out,
+                                      int64_t ldo, void *stream) {
+    SGLM_CHECK_ARG(T >= 0 && n_cols_in > 0 && n_cols_out >= 0 && n_rows >= 0 && ldx >= n_cols_in && ldo >= n_cols_out,
+                   SGLM_E_SHAPE, "timeshift_rows: bad shape");
+    if (n_rows == 0 || n_cols_out == 0) return SGLM_OK;
+    SGLM_CHECK_ARG(X && col_src && col_shift && rows && out, SGLM_E_INVALID_ARG, "timeshift_rows: null pointer");
+    const long long total = n_rows * (long long)n_cols_out;
+    const int grid = (int)std::min<long long>(ceil_div<long long>(total, TS_THREADS), (long long)sm_count() * 32);
+    timeshift_rows_kernel<<<grid, TS_THREADS, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint64_t *>(X), T, ldx, col_src, col_shift, n_cols_out, fill_bits,
+        (const long long *)rows, n_rows, reinterpret_cast<uint64_t *>(out), ldo);
+    SGLM_LAUNCH_OK("timeshift_rows_kernel");
+    return SGLM_OK;
+}
+
+extern "C" int sglm_lag_valid_rows(const double *X, int64_t T, int32_t n_cols_in, int64_t ldx,
+                                   const int32_t *col_src, const int32_t *col_shift, int32_t n_cols_out,
+                                   int32_t shift_min, int32_t shift_max, int32_t fill_is_nan, uint8_t *valid,
+                                   int64_t *summary3, void *stream) {
+    SGLM_CHECK_ARG(T >= 0 && n_cols_in > 0 && n_cols_out >= 0 && ldx >= n_cols_in, SGLM_E_SHAPE, "lag_valid_rows: bad shape");
+    SGLM_CHECK_ARG(valid && summary3 && (n_cols_out == 0 || (col_src && col_shift)), SGLM_E_INVALID_ARG,
+                   "lag_valid_rows: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long init[3] = {0, (long long)T, -1};
+    SGLM_CUDA_OK(cudaMemcpyAsync(summary3, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    SGLM_CUDA_OK(cudaStreamSynchronize(st));       // `init` lives on this frame
+    if (T == 0) return SGLM_OK;
+    const int grid = (int)std::min<long long>(ceil_div<long long>(T, 256), (long long)sm_count() * 16);
+    if (n_cols_out == 0) { shift_min = 0; shift_max = 0; }
+    lag_valid_init_kernel<<<grid, 256, 0, st>>>(valid, T, shift_min, shift_max, fill_is_nan);
+    SGLM_LAUNCH_OK("lag_valid_init_kernel");
+    if (n_cols_out > 0) {
+        SGLM_CHECK_ARG(X != nullptr, SGLM_E_INVALID_ARG, "lag_valid_rows: null X");
+        const long long total = T * (long long)n_cols_in;
+        const int g2 = (int)std::min<long long>(ceil_div<long long>(total, 256), (long long)sm_count() * 32);
+        lag_valid_scatter_kernel<<<g2, 256, 0, st>>>(X, T, n_cols_in, ldx, col_src, col_shift, n_cols_out, valid);
+        SGLM_LAUNCH_OK("lag_valid_scatter_kernel");
+    }
+    mask_summary_kernel<<<grid, 256, 0, st>>>(valid, T, (long long *)summary3);
+    SGLM_LAUNCH_OK("mask_summary_kernel");
+    return SGLM_OK;
+}
+
+extern "C" int sglm_index_mask_u8(const int64_t *idx, int64_t n_idx, uint8_t *mask, int64_t T, int32_t *dup_flag,
+                                  void *stream) {
+    SGLM_CHECK_ARG(n_idx >= 0 && T >= 0, SGLM_E_SHAPE, "index_mask: negative size");
+    SGLM_CHECK_ARG(mask && dup_flag && (n_idx == 0 || idx), SGLM_E_INVALID_ARG, "index_mask: null pointer");
+    SGLM_CHECK_ARG(((uintptr_t)mask & 3) == 0, SGLM_E_ALIGN, "index_mask: mask must be 4-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    SGLM_CUDA_OK(cudaMemsetAsync(mask, 0, (size_t)((T + 3) / 4 * 4), st));     // mask holds T rounded up to 4 bytes
+    SGLM_CUDA_OK(cudaMemsetAsync(dup_flag, 0, sizeof(int), st));
+    if (n_idx == 0) return SGLM_OK;
+    const int grid = (int)std::min<long long>(ceil_div<long long>(n_idx, 256), (long long)sm_count() * 16);
+    index_mask_kernel<<<grid, 256, 0, st>>>((const long long *)idx, n_idx, (unsigned *)mask, T, dup_flag);
+    SGLM_LAUNCH_OK("index_mask_kernel");
+    return SGLM_OK;
+}
+
+extern "C" int sglm_roll_f64(const double *y, int64_t n, int64_t shift, double *out, void *stream) {
+    SGLM_CHECK_ARG(n >= 0, SGLM_E_SHAPE, "roll: negative size");
+    if (n == 0) return SGLM_OK;
+    SGLM_CHECK_ARG(y && out && y != out, SGLM_E_INVALID_ARG, "roll: null or aliased pointer");
+    long long s = shift % n;
+    if (s < 0) s += n;
+    const int grid = (int)std::min<long long>(ceil_div<long long>(n, 256), (long long)sm_count() * 16);
+    roll_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, n, s, out);
+    SGLM_LAUNCH_OK("roll_kernel");
+    return SGLM_OK;
+}
+
+extern "C" size_t sglm_mask_compact_workspace_bytes(int64_t T) {
+    return (size_t)std::max<long long>(1, ceil_div<long long>(T, CMP_CH)) * sizeof(long long);
+}
+
+extern "C" int sglm_mask_compact_rows(const uint8_t *valid, int64_t T, int64_t *rows, void *workspace,
+                                      size_t workspace_bytes, void *stream) {
+    SGLM_CHECK_ARG(T >= 0, SGLM_E_SHAPE, "mask_compact: bad shape");
+    if (T == 0) return SGLM_OK;
+    SGLM_CHECK_ARG(valid && rows && workspace, SGLM_E_INVALID_ARG, "mask_compact: null pointer");
+    const long long nb = ceil_div<long long>(T, CMP_CH);
+    SGLM_CHECK_ARG(workspace_bytes >= (size_t)nb * sizeof(long long), SGLM_E_WORKSPACE, "mask_compact: workspace too small");
+    SGLM_CHECK_ARG(nb <= 0x7fffffffLL, SGLM_E_SHAPE, "mask_compact: too many rows");
+    cudaStream_t st = (cudaStream_t)stream;
+    long long *offs = (long long *)workspace;
+    mask_block_count_kernel<<<(unsigned)nb, 256, 0, st>>>(valid, T, offs);
+    SGLM_LAUNCH_OK("mask_block_count_kernel");
+    exclusive_scan_kernel<<<1, 1024, 0, st>>>(offs, nb);
+    SGLM_LAUNCH_OK("exclusive_scan_kernel");
+    mask_compact_kernel<<<(unsigned)nb, 256, 0, st>>>(valid, T, offs, (long long *)rows);
+    SGLM_LAUNCH_OK("mask_compact_kernel");
+    return SGLM_OK;
 }
 
 extern "C" int sglm_crop_rows_f64(const double *X, int64_t ldx, int64_t row_begin, int64_t n_rows,

@@ -50,6 +50,44 @@ class SGLM_worker():
 # --------------------------------------------------------------------------- #
 # the batched plan
 # --------------------------------------------------------------------------- #
+def _normalise_cv_idx(cv_idx, T):
+    """Fold index lists as the reference uses them (X[idx, :], backend/sglm_cv.py:106-110): boolean masks become
+    positions, negative positions wrap, anything outside [-T, T) raises IndexError as numpy does.  Host lists stay
+    numpy int64 arrays, CUDA tensors stay on the device (one fused range check for all of them)."""
+    import torch
+    out, checks = [], []
+    for pair in cv_idx:
+        norm = []
+        for idx in pair:
+            if eng.is_torch(idx):
+                t = idx.reshape(-1)
+                if t.dtype == torch.bool:
+                    if t.numel() != T:
+                        raise IndexError(f"boolean index did not match indexed array along axis 0; size of axis is {T} "
+                                         f"but size of corresponding boolean axis is {t.numel()}")
+                    t = torch.nonzero(t).reshape(-1)
+                t = t.to(device="cuda", dtype=torch.int64)
+                if t.numel():
+                    checks.append(((t < -T) | (t >= T)).any())
+                norm.append(torch.where(t < 0, t + T, t))
+            else:
+                a = np.asarray(idx).reshape(-1)
+                if a.dtype == bool:
+                    if a.shape[0] != T:
+                        raise IndexError(f"boolean index did not match indexed array along axis 0; size of axis is {T} "
+                                         f"but size of corresponding boolean axis is {a.shape[0]}")
+                    a = np.flatnonzero(a)
+                a = a.astype(np.int64, copy=False)
+                if a.size and (a.min() < -T or a.max() >= T):
+                    bad = a[(a < -T) | (a >= T)][0]
+                    raise IndexError(f"index {int(bad)} is out of bounds for axis 0 with size {T}")
+                norm.append(np.where(a < 0, a + T, a))
+        out.append(tuple(norm))
+    if checks and bool(torch.stack(checks).any().item()):
+        raise IndexError(f"index out of bounds for axis 0 with size {T}")
+    return out
+
+
 def _fold_weights(cv_idx, T):
     """Row multiplicities of every train / test index list (X[idx,:] semantics) and whether
     each train set is exactly the complement of its test set (then train = full - test)."""
@@ -79,198 +117,313 @@ def _use_tensor_core_gram(T, C):
 
 def _unique_sorted_rows(cv_idx, T):
     """Sorted, duplicate-free test rows per fold as CUDA int64 tensors, or None when a test
-    list repeats rows (then the weighted fp64 path is used)."""
+    list repeats rows (then the weighted fp64 path is used).  The lists were normalised by
+    _normalise_cv_idx (positions in [0, T))."""
     import torch
-    out = []
+    ts = []
     for (_, test) in cv_idx:
-        t = test if eng.is_torch(test) else torch.from_numpy(np.ascontiguousarray(np.asarray(test).reshape(-1), dtype=np.int64))
-        t = t.to(device="cuda", dtype=torch.int64)
-        t = torch.where(t < 0, t + T, t)
-        u = torch.unique(t, sorted=True)
+        t = test if eng.is_torch(test) else torch.from_numpy(np.ascontiguousarray(test, dtype=np.int64))
+        ts.append(t.to(device="cuda", dtype=torch.int64))
+    if not ts:
+        return []
+    # one read-back for all folds: is the list already ascending and duplicate-free (the usual case)?
+    asc = torch.stack([(t[1:] > t[:-1]).all() if t.numel() > 1 else torch.ones((), dtype=torch.bool, device="cuda")
+                       for t in ts]).cpu().numpy()
+    out = []
+    for t, ok in zip(ts, asc):
+        if ok:
+            out.append(t)
+            continue
+        u = eng.sorted_unique_rows(t, T)
         if u.numel() != t.numel():
             return None
         out.append(u)
     return out
 
 
+class GaussianSession:
+    """One cross-validation problem of Gaussian-family GLMs — (X, y, folds, parameter sets) — cut into the stages
+    of the batched plan, so that the stages of SEVERAL problems can be batched (multi-session grids: one
+    coordinate-descent launch for all sessions' models) or spread over GPUs (sglm_dist: statistics row-sharded
+    and all-reduced, models dealt to ranks):
+
+        build_statistics()  G[s] for s = full data, every test fold (train = full - test), explicit train sets
+        model_specs()       one ModelSpec per (parameter set, fold) + per refit, set-major
+        score(W, sel)       intercepts and train / test / full RSS of the models `sel` from the statistics
+        assemble(...)       the reference's result dicts (backend/sglm_cv.py:188-200)"""
+
+    def __init__(self, Xd, yd, cv_idx, glms, rolls, score_method):
+        import torch
+        self.Xd, self.yd, self.glms, self.rolls, self.score_method = Xd, yd, glms, rolls, score_method
+        self.T, self.C = Xd.shape
+        T = self.T
+        self.cv_idx = cv_idx
+        self.F = len(cv_idx)
+        # y columns: column 0 = un-rolled y (refit, backend/sglm_cv.py:181), then one per distinct roll
+        roll_vals = [0] + sorted({r for r in rolls if r % max(T, 1) != 0})
+        self.ycol_of_roll = {}
+        cols = []
+        for k, r in enumerate(roll_vals):
+            cols.append(yd if k == 0 else eng.roll_vector(yd, int(r)))
+            self.ycol_of_roll[r] = k
+        for r in rolls:
+            if r % max(T, 1) == 0:
+                self.ycol_of_roll[r] = 0
+        self.Yd = torch.stack(cols, dim=1).contiguous() if len(cols) > 1 else yd.reshape(-1, 1)
+        self.n_y = self.Yd.shape[1]
+        self.G = None
+        self.problems = {}
+
+    # ------------------------------------------------------------------ statistics
+    def fold_sets(self):
+        """Row sets of the statistics: (n_te, n_tr, extra, test_rows | None).  extra = folds whose train rows are
+        not the complement of their test rows (they get explicit train statistics)."""
+        tr_w, te_w, n_tr, n_te, comp = _fold_weights(self.cv_idx, self.T)
+        self.n_te, self.n_tr = n_te, n_tr
+        self.extra = [f for f in range(self.F) if not comp[f]]
+        self.train_set = {f: (1 + self.F + self.extra.index(f)) if f in self.extra else None for f in range(self.F)}
+        return tr_w, te_w
+
+    def build_statistics(self, G=None):
+        """set 0 = full data, 1..F = test folds, then explicit train sets.  `G` given: statistics computed
+        elsewhere (the row-sharded, all-reduced Gram of sglm_dist)."""
+        import torch
+        T, C, F = self.T, self.C, self.F
+        tr_w, te_w = self.fold_sets()
+        if G is None and not self.extra and _use_tensor_core_gram(T, C):
+            # 0/1 row sets: tcgen05 int8 digit-plane Gram (exact integer accumulation, fp64 result)
+            test_rows = _unique_sorted_rows(self.cv_idx, T)
+            if test_rows is not None:
+                G, _ = eng.suffstats_tc(self.Xd, self.Yd, [None] + test_rows)
+        if G is None:
+            # general row multiplicities: fp64 DMMA Gram with row weights (at most 64 row sets per launch)
+            w_rows = [None] + te_w + [tr_w[f] for f in self.extra]
+            rows_hint = [T] + self.n_te + [self.n_tr[f] for f in self.extra]
+            parts = []
+            for c0 in range(0, len(w_rows), 64):
+                chunk = w_rows[c0:c0 + 64]
+                if len(chunk) == 1 and chunk[0] is None:
+                    W = None
+                else:
+                    W = torch.stack([torch.ones_like(self.yd) if w is None else w for w in chunk]).contiguous()
+                parts.append(eng.suffstats(self.Xd, self.Yd, W, rows_hint[c0:c0 + 64]))
+            G = parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)
+        self.G = G
+        self.finite_flag = torch.isfinite(G[0]).all()            # read back together with the results
+        return G
+
+    def problem(self, fold, ycol, fi):
+        key = (fold, ycol, bool(fi))
+        if key not in self.problems:
+            G, C, n_y, T = self.G, self.C, self.n_y, self.T
+            if fold is None:
+                p = eng.center(G[0], None, C, n_y, ycol, fi, n_rows=T)
+            elif self.train_set[fold] is None:
+                p = eng.center(G[0], G[1 + fold], C, n_y, ycol, fi, n_rows=T - self.n_te[fold])
+            else:
+                p = eng.center(G[self.train_set[fold]], None, C, n_y, ycol, fi, n_rows=self.n_tr[fold])
+            self.problems[key] = p
+        return self.problems[key]
+
+    def model_specs(self):
+        """ModelSpecs in set-major order: the F fold fits of a set, then its full-data refit."""
+        specs, self.owner = [], []            # owner[i] = (param set k, fold f or None)
+        for k, (glm, r) in enumerate(zip(self.glms, self.rolls)):
+            est = glm.model
+            est._check_supported()
+            for f in list(range(self.F)) + [None]:
+                p = self.problem(f, self.ycol_of_roll[r] if f is not None else 0, est.fit_intercept)
+                specs.append(est._spec(p))    # no device read-back: row counts are known on the host
+                self.owner.append((k, f))
+        self.models = specs
+        return specs
+
+    # ------------------------------------------------------------------ scores from the statistics
+    def score(self, Wd, sel=None):
+        """Intercepts and residual sums of squares of the models `sel` (indices into model_specs(); default all),
+        whose coefficients are the rows of Wd: RSS(set) = V' G[set] V.  Returns device tensors
+        (b, rss_full, rss_test, rss_train), each [len(sel)]."""
+        import torch
+        sel = list(range(len(self.models))) if sel is None else list(sel)
+        models = [self.models[i] for i in sel]
+        b_d, V = eng.finalize(Wd, self.C, self.n_y, models)
+        M = len(models)
+        fold_of = np.array([-1 if self.owner[i][1] is None else self.owner[i][1] for i in sel])
+        rss_full = eng.quadform(self.G[0], V)
+        rss_test = torch.zeros(M, dtype=torch.float64, device="cuda")
+        rss_train = rss_full.clone()
+        for f in range(self.F):
+            pick = np.flatnonzero(fold_of == f)
+            if len(pick) == 0:
+                continue
+            pick_t = eng._dev(pick, np.int64)
+            Vf = V.index_select(0, pick_t)
+            q_te = eng.quadform(self.G[1 + f], Vf)
+            rss_test.index_copy_(0, pick_t, q_te)
+            if self.train_set[f] is None:
+                rss_train.index_copy_(0, pick_t, rss_full.index_select(0, pick_t) - q_te)
+            else:
+                rss_train.index_copy_(0, pick_t, eng.quadform(self.G[self.train_set[f]], Vf))
+        return b_d, rss_full, rss_test, rss_train
+
+    def moments(self):
+        """[set, (y cols | 1), (y cols | 1)] block of the statistics on the host (n, sum y, y'y of every row set)."""
+        C, n_y = self.C, self.n_y
+        return self.G[:, C:, C:C + n_y + 1].cpu().numpy()
+
+    # ------------------------------------------------------------------ result dicts
+    def assemble(self, coef_folds, coef_full, icpt, rss_test_h, rss_train_h, info, status, Gy=None):
+        """coef_folds [set][C][F], coef_full [set][C], icpt / rss_* / info / status per model (set-major), all on
+        the host -> the reference's per-set result dicts."""
+        if not bool(self.finite_flag.item()):
+            raise ValueError("Input contains NaN, infinity or a value too large for dtype('float64').")
+        glms, rolls, F, n_y = self.glms, self.rolls, self.F, self.n_y
+        ycol_of_roll, train_set, score_method = self.ycol_of_roll, self.train_set, self.score_method
+        n_sets_k = len(glms)
+        Gy = self.moments() if Gy is None else Gy
+
+        def set_moments(s, ycol):
+            return Gy[s, n_y, n_y], Gy[s, ycol, n_y], Gy[s, ycol, ycol]
+
+        # per-fold moments of every y column (vectorised over the folds; the loop below runs once per set)
+        mom = {}
+        for ycol in sorted(set(ycol_of_roll.values())):
+            n_f = np.array([set_moments(1 + f, ycol)[0] for f in range(F)])
+            sy_f = np.array([set_moments(1 + f, ycol)[1] for f in range(F)])
+            yy_f = np.array([set_moments(1 + f, ycol)[2] for f in range(F)])
+            n_t, sy_t, yy_t = np.zeros(F), np.zeros(F), np.zeros(F)
+            n0, sy0, yy0 = set_moments(0, ycol)
+            for f in range(F):
+                if train_set[f] is None:
+                    n_t[f], sy_t[f], yy_t[f] = n0 - n_f[f], sy0 - sy_f[f], yy0 - yy_f[f]
+                else:
+                    n_t[f], sy_t[f], yy_t[f] = set_moments(train_set[f], ycol)
+            with np.errstate(divide='ignore', invalid='ignore'):
+                tss_f = np.where(n_f > 0, yy_f - sy_f * sy_f / n_f, 0.0)
+                tss_t = np.where(n_t > 0, yy_t - sy_t * sy_t / n_t, 0.0)
+            mom[ycol] = (n_f, n_t, tss_f, tss_t)
+
+        def r2_vec(rss, tss):
+            with np.errstate(divide='ignore', invalid='ignore'):
+                return np.where(tss <= 0.0, np.where(rss == 0.0, 1.0, 0.0), 1.0 - rss / np.where(tss <= 0.0, 1.0, tss))
+
+        # scores of every (set, fold) at once
+        ycols = np.array([ycol_of_roll[r] for r in rolls], dtype=np.int64)
+        fi = np.array([bool(g.model.fit_intercept) for g in glms])
+        rte = np.maximum(rss_test_h.reshape(n_sets_k, F + 1)[:, :F], 0.0)
+        rtr = np.maximum(rss_train_h.reshape(n_sets_k, F + 1)[:, :F], 0.0)
+        icpt2 = icpt.reshape(n_sets_k, F + 1)
+        n_f = np.stack([mom[c][0] for c in ycols]) if n_sets_k else np.zeros((0, F))
+        n_t = np.stack([mom[c][1] for c in ycols]) if n_sets_k else np.zeros((0, F))
+        tss_f = np.stack([mom[c][2] for c in ycols]) if n_sets_k else np.zeros((0, F))
+        tss_t = np.stack([mom[c][3] for c in ycols]) if n_sets_k else np.zeros((0, F))
+        if score_method == 'r2':
+            S_tr, S_te = r2_vec(rtr, tss_t), r2_vec(rte, tss_f)
+        else:
+            with np.errstate(divide='ignore', invalid='ignore'):
+                S_tr, S_te = -rtr / n_t, -rte / n_f
+        rss_pool_a = np.zeros(n_sets_k)
+        tss_pool_a = np.zeros(n_sets_k)
+        n_pool_a = np.zeros(n_sets_k)
+        for f in range(F):                                   # left-to-right, as the reference accumulates fold by fold
+            rss_pool_a += rte[:, f]
+            tss_pool_a += np.maximum(tss_f[:, f], 0.0)
+            n_pool_a += n_f[:, f]
+        with np.errstate(divide='ignore', invalid='ignore'):
+            mean_tr = S_tr.mean(axis=1) if F else np.full(n_sets_k, np.nan)
+            mean_te = S_te.mean(axis=1) if F else np.full(n_sets_k, np.nan)
+            std_te = S_te.std(axis=1) if F else np.full(n_sets_k, np.nan)
+
+        results = []
+        for k, glm in enumerate(glms):
+            base = k * (F + 1)
+            rss_pool, tss_pool, n_pool = rss_pool_a[k], tss_pool_a[k], n_pool_a[k]
+            i_full = base + F
+            _set_fitted(glm, coef_full[k], icpt[i_full], info[i_full], status[i_full])
+            results.append({
+                'cv_coefs': coef_folds[k],
+                'cv_intercepts': icpt2[k, :F].copy() if fi[k] else np.zeros(F),
+                'cv_scores_train': S_tr[k].copy(),
+                'cv_scores_test': S_te[k].copy(),
+                'cv_mean_score_train': mean_tr[k],
+                'cv_mean_score': mean_te[k],
+                'cv_std_score': std_te[k],
+                'cv_R2_score': 0 if tss_pool == 0 else 1 - rss_pool / tss_pool,      # sglm.calc_R2
+                'cv_mse_score': rss_pool / n_pool if n_pool else np.nan,
+                'model': glm,
+                '_fit_info': {'cd_info': info[base:base + F + 1], 'status': status[base:base + F + 1]},
+            })
+            bad = status[base:base + F + 1]
+            if np.any(bad == 2):
+                raise np.linalg.LinAlgError("Matrix is singular: X'X + alpha*I is not positive definite")
+        return results
+
+    def download_and_assemble(self, Wd, b_d, rss_test, rss_train, info, status):
+        """Coefficients leave the device already in the layout of the result dicts: [set][C][F] for the folds
+        (cv_coefs is C x F, backend/sglm_cv.py:98) and [set][C] for the refits — one transposition on the device
+        instead of one per parameter set on the host."""
+        C, F = self.C, self.F
+        n_sets_k = len(self.glms)
+        W3 = Wd[:, :C].reshape(n_sets_k, F + 1, C)
+        coef_folds = W3[:, :F, :].permute(0, 2, 1).contiguous().cpu().numpy()      # [set][C][F]
+        coef_full = W3[:, F, :].contiguous().cpu().numpy()                          # [set][C]
+        return self.assemble(coef_folds, coef_full, b_d.cpu().numpy(), rss_test.cpu().numpy(),
+                             rss_train.cpu().numpy(), info, status)
+
+
 def _gaussian_grid(Xd, yd, cv_idx, glms, rolls, score_method):
     """Fit every (param set, fold) + every full-data refit of Gaussian-family GLMs.
     glms: list of sglm_.GLM objects (already dispatched to an estimator class)."""
-    import torch
-    T, C = Xd.shape
-    F = len(cv_idx)
-    # y columns: column 0 = un-rolled y (refit, backend/sglm_cv.py:181), then one per distinct roll
-    roll_vals = [0] + sorted({r for r in rolls if r % max(T, 1) != 0})
-    ycol_of_roll = {}
-    cols = []
-    for k, r in enumerate(roll_vals):
-        cols.append(yd if k == 0 else torch.roll(yd, int(r)))
-        ycol_of_roll[r] = k
-    for r in rolls:
-        if r % max(T, 1) == 0:
-            ycol_of_roll[r] = 0
-    Yd = torch.stack(cols, dim=1).contiguous()
-    n_y = Yd.shape[1]
+    ses = GaussianSession(Xd, yd, cv_idx, glms, rolls, score_method)
+    ses.build_statistics()
+    models = ses.model_specs()
+    Wd, info, status = eng.solve_models(models, ses.C)
+    b_d, _, rss_test, rss_train = ses.score(Wd)
+    return ses.download_and_assemble(Wd, b_d, rss_test, rss_train, info, status)
 
-    tr_w, te_w, n_tr, n_te, comp = _fold_weights(cv_idx, T)
-    # statistics: set 0 = full data, 1..F = test folds, then explicit train sets where the
-    # train rows are not the complement of the test rows
-    extra = [f for f in range(F) if not comp[f]]
-    G = None
-    if not extra and _use_tensor_core_gram(T, C):
-        # 0/1 row sets: tcgen05 int8 digit-plane Gram (exact integer accumulation, fp64 result)
-        test_rows = _unique_sorted_rows(cv_idx, T)
-        if test_rows is not None:
-            G, _ = eng.suffstats_tc(Xd, Yd, [None] + test_rows)
-    if G is None:
-        # general row multiplicities: fp64 DMMA Gram with row weights
-        w_rows = [torch.ones_like(yd)] + te_w + [tr_w[f] for f in extra]
-        rows_hint = [T] + n_te + [n_tr[f] for f in extra]
-        W = torch.stack(w_rows).contiguous() if len(w_rows) > 1 else None
-        G = eng.suffstats(Xd, Yd, W, rows_hint)
-        del w_rows, W
-    finite_flag = torch.isfinite(G[0]).all()            # read back together with the results
-    train_set = {f: (1 + F + extra.index(f)) if f in extra else None for f in range(F)}
-    del tr_w
 
-    # centred problems, shared by every model with the same (row set, y column, intercept)
-    problems = {}
-
-    def problem(fold, ycol, fi):
-        key = (fold, ycol, bool(fi))
-        if key not in problems:
-            if fold is None:
-                p = eng.center(G[0], None, C, n_y, ycol, fi, n_rows=T)
-            elif train_set[fold] is None:
-                p = eng.center(G[0], G[1 + fold], C, n_y, ycol, fi, n_rows=T - n_te[fold])
-            else:
-                p = eng.center(G[train_set[fold]], None, C, n_y, ycol, fi, n_rows=n_tr[fold])
-            problems[key] = p
-        return problems[key]
-
-    specs, owner = [], []            # owner[i] = (param set k, fold f or None)
-    for k, (glm, r) in enumerate(zip(glms, rolls)):
-        est = glm.model
-        est._check_supported()
-        for f in list(range(F)) + [None]:
-            p = problem(f, ycol_of_roll[r] if f is not None else 0, est.fit_intercept)
-            specs.append((est, p))
-            owner.append((k, f))
-    models = [est._spec(p) for est, p in specs]         # no device read-back: row counts are known on the host
-    Wd, info, status = eng.solve_models(models, C)
-    b_d, V = eng.finalize(Wd, C, n_y, models)
-
-    # residual sums of squares from the statistics: RSS(set) = V' G[set] V
-    M = len(models)
-    fold_of = np.array([-1 if f is None else f for (_, f) in owner])
-    rss_full = eng.quadform(G[0], V)
-    rss_test = torch.zeros(M, dtype=torch.float64, device="cuda")
-    rss_train = rss_full.clone()
-    for f in range(F):
-        sel = np.flatnonzero(fold_of == f)
-        if len(sel) == 0:
-            continue
-        sel_t = eng._dev(sel, np.int64)
-        Vf = V.index_select(0, sel_t)
-        q_te = eng.quadform(G[1 + f], Vf)
-        rss_test.index_copy_(0, sel_t, q_te)
-        if train_set[f] is None:
-            rss_train.index_copy_(0, sel_t, rss_full.index_select(0, sel_t) - q_te)
-        else:
-            rss_train.index_copy_(0, sel_t, eng.quadform(G[train_set[f]], Vf))
-
-    if not bool(finite_flag.item()):
-        raise ValueError("Input contains NaN, infinity or a value too large for dtype('float64').")
-    n_sets_k = len(glms)
-    # coefficients leave the device already in the layout of the result dicts: [set][C][F] for the folds
-    # (cv_coefs is C x F, backend/sglm_cv.py:98) and [set][C] for the refits — one transposition on the
-    # device instead of one per parameter set on the host
-    W3 = Wd[:, :C].reshape(n_sets_k, F + 1, C)
-    coef_folds = W3[:, :F, :].permute(0, 2, 1).contiguous().cpu().numpy()      # [set][C][F]
-    coef_full = W3[:, F, :].contiguous().cpu().numpy()                          # [set][C]
-    icpt = b_d.cpu().numpy()
-    rss_test_h = rss_test.cpu().numpy()
-    rss_train_h = rss_train.cpu().numpy()
-    Gy = G[:, C:, C:C + n_y + 1].cpu().numpy()      # [set, (y cols | 1), (y cols | 1)]
-
-    def set_moments(s, ycol):
-        n = Gy[s, n_y, n_y]
-        sy = Gy[s, ycol, n_y]
-        yy = Gy[s, ycol, ycol]
-        return n, sy, yy
-
-    # per-fold moments of every y column (vectorised over the folds; the loop below runs once per set)
-    mom = {}
-    for ycol in sorted(set(ycol_of_roll.values())):
-        n_f = np.array([set_moments(1 + f, ycol)[0] for f in range(F)])
-        sy_f = np.array([set_moments(1 + f, ycol)[1] for f in range(F)])
-        yy_f = np.array([set_moments(1 + f, ycol)[2] for f in range(F)])
-        n_t, sy_t, yy_t = np.zeros(F), np.zeros(F), np.zeros(F)
-        n0, sy0, yy0 = set_moments(0, ycol)
-        for f in range(F):
-            if train_set[f] is None:
-                n_t[f], sy_t[f], yy_t[f] = n0 - n_f[f], sy0 - sy_f[f], yy0 - yy_f[f]
-            else:
-                n_t[f], sy_t[f], yy_t[f] = set_moments(train_set[f], ycol)
-        with np.errstate(divide='ignore', invalid='ignore'):
-            tss_f = np.where(n_f > 0, yy_f - sy_f * sy_f / n_f, 0.0)
-            tss_t = np.where(n_t > 0, yy_t - sy_t * sy_t / n_t, 0.0)
-        mom[ycol] = (n_f, n_t, tss_f, tss_t)
-
-    def r2_vec(rss, tss):
-        with np.errstate(divide='ignore', invalid='ignore'):
-            return np.where(tss <= 0.0, np.where(rss == 0.0, 1.0, 0.0), 1.0 - rss / np.where(tss <= 0.0, 1.0, tss))
-
-    # scores of every (set, fold) at once
-    ycols = np.array([ycol_of_roll[r] for r in rolls], dtype=np.int64)
-    fi = np.array([bool(g.model.fit_intercept) for g in glms])
-    rte = np.maximum(rss_test_h.reshape(n_sets_k, F + 1)[:, :F], 0.0)
-    rtr = np.maximum(rss_train_h.reshape(n_sets_k, F + 1)[:, :F], 0.0)
-    icpt2 = icpt.reshape(n_sets_k, F + 1)
-    n_f = np.stack([mom[c][0] for c in ycols]) if n_sets_k else np.zeros((0, F))
-    n_t = np.stack([mom[c][1] for c in ycols]) if n_sets_k else np.zeros((0, F))
-    tss_f = np.stack([mom[c][2] for c in ycols]) if n_sets_k else np.zeros((0, F))
-    tss_t = np.stack([mom[c][3] for c in ycols]) if n_sets_k else np.zeros((0, F))
-    if score_method == 'r2':
-        S_tr, S_te = r2_vec(rtr, tss_t), r2_vec(rte, tss_f)
-    else:
-        with np.errstate(divide='ignore', invalid='ignore'):
-            S_tr, S_te = -rtr / n_t, -rte / n_f
-    rss_pool_a = np.zeros(n_sets_k)
-    tss_pool_a = np.zeros(n_sets_k)
-    n_pool_a = np.zeros(n_sets_k)
-    for f in range(F):                                   # left-to-right, as the reference accumulates fold by fold
-        rss_pool_a += rte[:, f]
-        tss_pool_a += np.maximum(tss_f[:, f], 0.0)
-        n_pool_a += n_f[:, f]
-    with np.errstate(divide='ignore', invalid='ignore'):
-        mean_tr = S_tr.mean(axis=1) if F else np.full(n_sets_k, np.nan)
-        mean_te = S_te.mean(axis=1) if F else np.full(n_sets_k, np.nan)
-        std_te = S_te.std(axis=1) if F else np.full(n_sets_k, np.nan)
-
-    results = []
-    for k, glm in enumerate(glms):
-        base = k * (F + 1)
-        rss_pool, tss_pool, n_pool = rss_pool_a[k], tss_pool_a[k], n_pool_a[k]
-        i_full = base + F
-        _set_fitted(glm, coef_full[k], icpt[i_full], info[i_full], status[i_full])
-        results.append({
-            'cv_coefs': coef_folds[k],
-            'cv_intercepts': icpt2[k, :F].copy() if fi[k] else np.zeros(F),
-            'cv_scores_train': S_tr[k].copy(),
-            'cv_scores_test': S_te[k].copy(),
-            'cv_mean_score_train': mean_tr[k],
-            'cv_mean_score': mean_te[k],
-            'cv_std_score': std_te[k],
-            'cv_R2_score': 0 if tss_pool == 0 else 1 - rss_pool / tss_pool,      # sglm.calc_R2
-            'cv_mse_score': rss_pool / n_pool if n_pool else np.nan,
-            'model': glm,
-            '_fit_info': {'cd_info': info[base:base + F + 1], 'status': status[base:base + F + 1]},
-        })
-        bad = status[base:base + F + 1]
-        if np.any(bad == 2):
-            raise np.linalg.LinAlgError("Matrix is singular: X'X + alpha*I is not positive definite")
-    return results
+def cv_glm_mult_params_sessions(sessions, model_name, glm_kwarg_lst, verbose=0, score_method='mse'):
+    """Extension (BASELINE configs[4]): the same parameter grid on SEVERAL independent sessions
+    — `sessions` = [(X, y, cv_idx), ...] with the same number of design columns — as ONE batched plan: the
+    statistics of every session, then one coordinate-descent launch (and one Cholesky launch per problem) over
+    the models of all sessions, so that the heavy-tailed models of one session overlap the light ones of the
+    others.  Returns [cv_glm_mult_params-style dict per session]; each equals what a separate call returns."""
+    per_session = []
+    all_models = []
+    for (X, y, cv_idx) in sessions:
+        entries = []
+        for glm_kwargs in glm_kwarg_lst:
+            kw = dict(glm_kwargs)
+            name = kw.pop('model_name', model_name if model_name is not None else 'Gaussian')
+            entries.append((name, kw))
+        Xd, yd = eng.device_matrix(X), eng.device_vector(y)
+        if Xd.shape[0] != yd.shape[0]:
+            raise ValueError(f"Found input variables with inconsistent numbers of samples: [{Xd.shape[0]}, {yd.shape[0]}]")
+        cv = _normalise_cv_idx(list(cv_idx), Xd.shape[0])
+        glms, rolls = [], []
+        for name, kw in entries:
+            rolls.append(int(kw.pop('roll', 0)))
+            glms.append(sglm_.GLM(name, **kw))
+            if glms[-1].model.kind not in ("ols", "ridge", "lasso", "enet"):
+                raise NotImplementedError("cv_glm_mult_params_sessions batches the Gaussian family")
+        ses = GaussianSession(Xd, yd, cv, glms, rolls, score_method)
+        ses.build_statistics()
+        models = ses.model_specs()
+        per_session.append((ses, entries, len(all_models), len(models)))
+        all_models.extend(models)
+    C = per_session[0][0].C if per_session else 0
+    if any(ses.C != C for ses, _, _, _ in per_session):
+        raise ValueError("cv_glm_mult_params_sessions: every session must have the same number of design columns")
+    Wd, info, status = eng.solve_models(all_models, C)
+    out = []
+    for ses, entries, m0, m in per_session:
+        Ws = Wd[m0:m0 + m]
+        b_d, _, rss_test, rss_train = ses.score(Ws)
+        res = ses.download_and_assemble(Ws, b_d, rss_test, rss_train, info[m0:m0 + m], status[m0:m0 + m])
+        for (name, kw), r in zip(entries, res):
+            r['glm_kwargs'] = kw
+        out.append(_select_best([_order_result(r) for r in res], score_method))
+    return out
 
 
 def _r2(rss, tss):
@@ -351,7 +504,7 @@ def _cv_batch(X, y, cv_idx, entries, beta_, beta0_, score_method):
     yd = eng.device_vector(y)
     if Xd.shape[0] != yd.shape[0]:
         raise ValueError(f"Found input variables with inconsistent numbers of samples: [{Xd.shape[0]}, {yd.shape[0]}]")
-    cv_idx = list(cv_idx)
+    cv_idx = _normalise_cv_idx(list(cv_idx), Xd.shape[0])
     glms, rolls = [], []
     for model_name, kw in entries:
         rolls.append(int(kw.pop('roll', 0)))                          # backend/sglm_cv.py:95
@@ -410,6 +563,11 @@ def cv_glm_mult_params(X, y, cv_idx, model_name, glm_kwarg_lst, verbose=0, score
         for r in resp:
             print(f"{r['glm_kwargs']}\n> cv_mean_score_train: {r['cv_mean_score_train']}\n> cv_R2_score: "
                   f"{r['cv_R2_score']}\n> cv_mean_score: {r['cv_mean_score']}")
+    return _select_best(resp, score_method)
+
+
+def _select_best(resp, score_method):
+    """The reference's selection: strict '>' in list order (backend/sglm_cv.py:402-415)."""
     best_score = -np.inf
     best_params = None
     for cv_result in resp:

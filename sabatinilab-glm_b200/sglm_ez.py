@@ -18,11 +18,14 @@ def _shift_list(neg_order, pos_order):
     return [0] + list(range(neg_order, 0)) + list(range(1, pos_order + 1))
 
 
-def timeshift_cols(X, cols_to_shift, neg_order=0, pos_order=1):
+def timeshift_cols(X, cols_to_shift, neg_order=0, pos_order=1, device=None):
     """All shifts neg_order..pos_order of the named columns, un-shifted frame first
-    (backend/sglm_ez.py:102-123)."""
+    (backend/sglm_ez.py:102-123).  device=True (extension): a device-resident `sglm_pp.DeviceDesign`
+    instead of a host DataFrame — `dropna()`, column selection and the fits then run without the design
+    ever crossing PCIe."""
     col_nums = sglm_pp.get_column_nums(X, cols_to_shift)
-    return sglm_pp.timeshift_multiple(X, shift_inx=col_nums, shift_amt_list=_shift_list(neg_order, pos_order))
+    return sglm_pp.timeshift_multiple(X, shift_inx=col_nums, shift_amt_list=_shift_list(neg_order, pos_order),
+                                      device=device)
 
 
 def add_timeshifts_to_col_list(all_cols, shifted_cols, neg_order=0, pos_order=1):
@@ -60,15 +63,21 @@ def add_timeshifts_by_sl_to_col_list(all_cols, shifted_cols, sft_orders):
     added = []
     for col in shifted_cols:
         neg, pos = sft_orders[col]
-        added.extend(col + f'_{s}' for s in neg + pos)
+        # same naming rule as sglm_pp.timeshift_multiple: integral shift amounts are written as integers
+        added.extend(col + f'_{int(s) if float(s).is_integer() else s}' for s in neg + pos)
     return all_cols + added
 
 
 def fit_GLM(X, y, model_name='Gaussian', *args, **kwargs):
     """Fit one GLM on DataFrame X / Series y (backend/sglm_ez.py:149-171)."""
     glm = sglm_.GLM(model_name, *args, **kwargs)
-    glm.fit(X.values, y.values)
+    glm.fit(_vals(X), _vals(y))
     return glm
+
+
+def _vals(x):
+    """`.values` of a DataFrame / Series (backend/sglm_ez.py:376-377); a device-resident design stays as it is."""
+    return x if isinstance(x, sglm_pp.DeviceDesign) else x.values
 
 
 def diff_cols(X, cols, append_to_base=True):
@@ -128,7 +137,7 @@ def holdout_split_by_trial_id(X, y=None, id_cols=['nTrial', 'iBlock'], strat_col
 def simple_cv_fit(X, y, cv_idx, glm_kwarg_lst, model_type='Normal', verbose=0, score_method='mse'):
     """Grid search by cross-validation; returns (best_score, best_score_std, best_params,
     best_model, cv_results) (backend/sglm_ez.py:347-389)."""
-    cv_results = sglm_cv.cv_glm_mult_params(X.values, y.values, cv_idx, model_type, glm_kwarg_lst,
+    cv_results = sglm_cv.cv_glm_mult_params(_vals(X), _vals(y), cv_idx, model_type, glm_kwarg_lst,
                                             verbose=verbose, score_method=score_method)
     return (cv_results['best_score'], cv_results['best_score_std'], cv_results['best_params'],
             cv_results['best_model'], cv_results)

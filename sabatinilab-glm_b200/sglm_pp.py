@@ -85,6 +85,183 @@ def _restore_dtypes(res, X, src, sh):
 
 
 # --------------------------------------------------------------------------- #
+# device-resident design (numpy / pandas callers without the PCIe round trip)
+# --------------------------------------------------------------------------- #
+def _device_default():
+    import os
+    return os.environ.get("SGLM_DEVICE_DESIGN", "0") == "1"
+
+
+class DeviceDesign:
+    """Lag design that lives on the GPU: what `timeshift_multiple(..., device=True)` returns for
+    numpy / pandas input (or always with SGLM_DEVICE_DESIGN=1).
+
+    The reference hands the T x (P*L) design back as a host array, the drivers `dropna()` it, pick the
+    predictor and response columns and pass `.values` to the fit (er_refactored_from_scratch_cleanup.py:
+    421-452; backend/test/test_sglm_ez.py:23-41).  At 2M x 2000 that is a 32 GB matrix crossing PCIe
+    twice.  This object keeps the *recipe* instead — base signals on the device + column map + row
+    selection — and supports exactly those steps lazily:
+
+        d = sglm_pp.timeshift_multiple(X, ..., device=True)     # or sglm_ez.timeshift_cols(df, ..., device=True)
+        d = d.dropna()               # valid rows decided from the base signals (sglm_lag_valid_rows)
+        Xd, yd = d[x_cols], d[y_col] # column subsets of the map: free
+        sglm_cv.cv_glm_mult_params(Xd, yd, cv_idx, ...)          # gather runs here, on the device, valid rows only
+
+    Anything else sees an ordinary array: `np.asarray(d)`, `d.values`, `d.to_numpy()`, `d.to_pandas()`
+    materialise on the host (bit-identical to the reference's result)."""
+
+    def __init__(self, base, col_src, col_shift, fill_value, names=None, index=None, rows=None, n_base_rows=None):
+        self._base = base                                   # CUDA float64 [T, P]
+        self._src = np.ascontiguousarray(col_src, dtype=np.int32)
+        self._sh = np.ascontiguousarray(col_shift, dtype=np.int32)
+        self._fill = fill_value
+        self._names = None if names is None else list(names)
+        self._index = index                                 # pandas index of the base rows (or None)
+        self._rows = rows                                   # None (all rows) | (lo, hi) | CUDA int64 row list
+        self._T = int(base.shape[0]) if n_base_rows is None else int(n_base_rows)
+        self._cache = None
+
+    # ---- shape / labels
+    @property
+    def shape(self):
+        if self._rows is None:
+            n = self._T
+        elif isinstance(self._rows, tuple):
+            n = self._rows[1] - self._rows[0]
+        else:
+            n = int(self._rows.numel())
+        return (n, int(self._src.shape[0]))
+
+    def __len__(self):
+        return self.shape[0]
+
+    @property
+    def ndim(self):
+        return 2
+
+    @property
+    def dtype(self):
+        return np.dtype(np.float64)
+
+    @property
+    def columns(self):
+        return pd.Index(self._names) if self._names is not None else pd.RangeIndex(self.shape[1])
+
+    def row_positions(self):
+        """Positions (in the base signals) of the rows of this design, as a host int64 array."""
+        if self._rows is None:
+            return np.arange(self._T, dtype=np.int64)
+        if isinstance(self._rows, tuple):
+            return np.arange(self._rows[0], self._rows[1], dtype=np.int64)
+        return self._rows.cpu().numpy()
+
+    @property
+    def index(self):
+        pos = self.row_positions()
+        return self._index[pos] if self._index is not None else pd.RangeIndex(self._T)[pos]
+
+    # ---- lazy operations
+    def _derive(self, src=None, sh=None, names=None, rows="same"):
+        d = DeviceDesign(self._base, self._src if src is None else src, self._sh if sh is None else sh, self._fill,
+                         self._names if names is None else names, self._index,
+                         self._rows if isinstance(rows, str) else rows, self._T)
+        return d
+
+    def __getitem__(self, key):
+        """Column selection by name(s) (or integer positions for unnamed designs)."""
+        single = not isinstance(key, (list, tuple, np.ndarray, pd.Index))
+        keys = [key] if single else list(key)
+        if self._names is not None:
+            pos = []
+            for k in keys:
+                hits = [i for i, n in enumerate(self._names) if n == k]
+                if not hits:
+                    raise KeyError(k)
+                pos.extend(hits)
+        else:
+            pos = [int(k) for k in keys]
+        names = [self._names[i] for i in pos] if self._names is not None else None
+        out = self._derive(self._src[pos], self._sh[pos], names)
+        if names is None:
+            out._names = None
+        return out
+
+    def dropna(self):
+        """Rows without NaN (pandas `dropna()` / `X[~np.isnan(X).any(axis=1)]`), decided on the device from
+        the base signals and the column map — the dropped rows are never built."""
+        torch = nat.require_cuda()
+        T = self._T
+        valid = torch.empty(max(T, 1), dtype=torch.uint8, device="cuda")
+        summ = torch.empty(3, dtype=torch.int64, device="cuda")
+        C = int(self._src.shape[0])
+        both = eng._dev(np.concatenate([self._src, self._sh]), np.int32)
+        fill_nan = int(isinstance(self._fill, float) and np.isnan(self._fill)) if not hasattr(self._fill, "dtype") else int(np.isnan(self._fill))
+        nat.call("sglm_lag_valid_rows", nat.ptr(self._base), T, int(self._base.shape[1]), eng.row_stride(self._base),
+                 nat.ptr(both[:C]), nat.ptr(both[C:]), C, int(self._sh.min()) if C else 0, int(self._sh.max()) if C else 0,
+                 fill_nan, nat.ptr(valid), nat.ptr(summ), nat.stream_ptr())
+        if self._rows is not None:                          # an earlier selection: intersect
+            keep = torch.zeros(max(T, 1), dtype=torch.uint8, device="cuda")
+            if isinstance(self._rows, tuple):
+                keep[self._rows[0]:self._rows[1]] = 1
+            else:
+                keep[self._rows] = 1
+            valid &= keep
+            summ = torch.stack([valid[:T].sum(dtype=torch.int64), torch.tensor(T, device="cuda"), torch.tensor(-1, device="cuda")])
+            nz = torch.nonzero(valid[:T]).reshape(-1)
+            return self._derive(rows=nz)
+        cnt, first, last = (int(v) for v in summ.cpu().numpy())
+        if cnt == 0:
+            return self._derive(rows=(0, 0))
+        if last - first + 1 == cnt:
+            return self._derive(rows=(first, last + 1))
+        rows = torch.empty(cnt, dtype=torch.int64, device="cuda")
+        wb = nat.lib().sglm_mask_compact_workspace_bytes(T)
+        ws = torch.empty((wb + 7) // 8, dtype=torch.int64, device="cuda")
+        nat.call("sglm_mask_compact_rows", nat.ptr(valid), T, nat.ptr(rows), nat.ptr(ws), ws.numel() * 8, nat.stream_ptr())
+        return self._derive(rows=rows)
+
+    def copy(self):
+        return self._derive()
+
+    # ---- materialisation
+    def tensor(self):
+        """The design as a CUDA float64 tensor [rows, C] (built once, cached): plain gather + row view when
+        the rows are a contiguous range, row-list gather otherwise."""
+        if self._cache is None:
+            torch = nat.require_cuda()
+            if self._rows is None or isinstance(self._rows, tuple):
+                full = eng.gather(self._base, self._src, self._sh, self._fill)
+                self._cache = full if self._rows is None else full[self._rows[0]:self._rows[1]]
+            else:
+                n, C = self.shape
+                out = torch.empty((n, C), dtype=torch.float64, device="cuda")
+                if n and C:
+                    both = eng._dev(np.concatenate([self._src, self._sh]), np.int32)
+                    nat.call("sglm_timeshift_rows_f64", nat.ptr(self._base), self._T, int(self._base.shape[1]),
+                             eng.row_stride(self._base), nat.ptr(both[:C]), nat.ptr(both[C:]), C,
+                             nat.f64_bits(self._fill), nat.ptr(self._rows), n, nat.ptr(out), C, nat.stream_ptr())
+                self._cache = out
+        return self._cache
+
+    def to_numpy(self, dtype=None, copy=False):
+        a = self.tensor().cpu().numpy()
+        return a if dtype is None else a.astype(dtype)
+
+    def __array__(self, dtype=None, copy=None):
+        return self.to_numpy(dtype)
+
+    @property
+    def values(self):
+        return self.to_numpy()
+
+    def to_pandas(self):
+        return pd.DataFrame(self.to_numpy(), index=self.index, columns=self.columns)
+
+    def __repr__(self):
+        return f"DeviceDesign(shape={self.shape}, on cuda; np.asarray() / .to_pandas() materialise it)"
+
+
+# --------------------------------------------------------------------------- #
 # hot path
 # --------------------------------------------------------------------------- #
 def timeshift(X, shift_inx=[], shift_amt=1, keep_non_inx=False, dct=None, fill_value=np.nan):
@@ -119,7 +296,8 @@ def timeshift(X, shift_inx=[], shift_amt=1, keep_non_inx=False, dct=None, fill_v
     return res
 
 
-def timeshift_multiple(X, shift_inx=[], shift_amt_list=[-1, 0, 1], unshifted_keep_all=True, fill_value=np.nan):
+def timeshift_multiple(X, shift_inx=[], shift_amt_list=[-1, 0, 1], unshifted_keep_all=True, fill_value=np.nan,
+                       device=None):
     """All shifts of `shift_amt_list` as column blocks of one array, in list order; the
     zero-shift block keeps every column when `unshifted_keep_all`.  DataFrames get the
     reference's names: `col` for shift 0, f"{col}_{shift}" otherwise.
@@ -132,13 +310,22 @@ def timeshift_multiple(X, shift_inx=[], shift_amt_list=[-1, 0, 1], unshifted_kee
         raise ValueError("need at least one array to concatenate")
     if eng.is_torch(X):
         return eng.gather(eng.device_matrix(X), src, sh, fill_value)
+    if device is None:
+        device = _device_default()
+    names = None
     if is_df:
-        vals = _gather_host(X.values, src, sh, fill_value)
         names, pos = [], 0
         for a, n in zip(shift_amt_list, sizes):
             base = X.columns[src[pos:pos + n]]
             names.extend(list(base) if a == 0 else [f"{c}_{a}" for c in base])
             pos += n
+    if device:
+        # extension: the design stays on the GPU as a lazy DeviceDesign (see its docstring)
+        base_vals = X.values if is_df else np.asarray(X)
+        return DeviceDesign(eng.device_matrix(_to_f64_source(base_vals)), src, sh, fill_value, names,
+                            X.index if is_df else None)
+    if is_df:
+        vals = _gather_host(X.values, src, sh, fill_value)
         return _restore_dtypes(pd.DataFrame(vals, index=X.index, columns=names), X, src, sh)
     return _gather_host(np.asarray(X), src, sh, fill_value)
 

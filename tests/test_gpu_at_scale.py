@@ -1,0 +1,285 @@
+"""GPU tests at (near) BASELINE sizes — the code paths the benchmark runs and the reduced-size golden
+comparisons do not reach ("what's weak" 1):
+
+  * tcgen05 Gram with row lists far above one int32-safe segment (262 144 rows): multi-segment drains, K parts,
+    cell sums — bit-exact against the fp64 DMMA Gram on exactly representable data, 1e-12 on general data;
+  * the c3 shape at full width (2000 columns, 5 random folds, a cell above 262 144 rows): duality-gap rule and KKT
+    conditions from explicit residuals for the heaviest and the lightest models, fold scores against an explicit
+    pass over X, selection = argmax;
+  * the device-resident design (numpy in -> DeviceDesign -> dropna -> CV grid) equals the host path, also with NaNs
+    inside the base signals (row-list gather);
+  * several sessions batched into one launch plan (BASELINE configs[4] shape) equal the per-session calls.
+"""
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import coef_rel_err
+from oracle import sglm_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+import synth_data  # noqa: E402
+import _engine as eng  # noqa: E402
+import _sglm_native as nat  # noqa: E402
+import sglm_cv  # noqa: E402
+import sglm_ez  # noqa: E402
+import sglm_pp  # noqa: E402
+
+
+def test_tensor_core_gram_multi_segment_rows_vs_fp64_gram():
+    """1M x 64 mixed design, row sets of 1M / 700k / 450k rows (cells of 150k..450k rows: up to two int32-safe
+    segments per cell, several K parts).  Columns 0..55 hold values with <= 13 significant bits (0/1 indicators,
+    small dyadic rationals): every product sum stays below 2^53, so the fp64 DMMA Gram is EXACT and the digit-plane
+    Gram must equal it bit for bit.  Columns 56..63 are general doubles (8 digit planes): 1e-12 relative."""
+    T, C = 1_000_000, 64
+    rng = np.random.default_rng(7)
+    X = np.empty((T, C))
+    X[:, :40] = (rng.random((T, 40)) < 0.03)
+    X[:, 40:56] = np.round(rng.standard_normal((T, 16)) * 256.0) / 1024.0          # |x| < 2, multiples of 2^-10
+    X[:, 56:] = rng.standard_normal((T, 8))
+    y = np.round(rng.standard_normal(T) * 512.0) / 512.0
+    Xd, Yd = torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda()[:, None].contiguous()
+    perm = rng.permutation(T)
+    rows1 = torch.from_numpy(np.sort(perm[:700_000])).cuda()
+    rows2 = torch.from_numpy(np.sort(perm[550_000:])).cuda()                          # overlaps rows1 in 150k rows
+    G_tc, colS = eng.suffstats_tc(Xd, Yd, [None, rows1, rows2])
+    plan = dict(nat.last_tc_plan)
+    assert plan["cells"] and plan["k_parts"] > 1, plan
+    assert max(700_000 - 150_000, 450_000 - 150_000) > 262_144                        # a cell longer than one segment
+    W = torch.stack([torch.ones(T, dtype=torch.float64, device="cuda"), eng.index_counts(rows1, T),
+                     eng.index_counts(rows2, T)])
+    G_ref = eng.suffstats(Xd, Yd, W, [T, 700_000, 450_000])
+    torch.cuda.synchronize()
+    exact = list(range(56)) + [64, 65]                                                # exact columns + y + ones
+    ex = torch.tensor(exact, device="cuda")
+    a, b = G_tc[:, ex][:, :, ex], G_ref[:, ex][:, :, ex]
+    assert torch.equal(a, b), float((a - b).abs().max())
+    d = torch.sqrt(torch.diagonal(G_ref, dim1=1, dim2=2)[:, :C + 2])
+    rel = (G_tc[:, :C + 2, :C + 2] - G_ref[:, :C + 2, :C + 2]).abs() / (d[:, :, None] * d[:, None, :])
+    assert float(rel.max()) < 1e-12, float(rel.max())
+    # the same sets without the cell decomposition (one GEMM pass per set) give the same bits
+    old = eng.TC_CELLS
+    eng.TC_CELLS = False
+    try:
+        G_sets, _ = eng.suffstats_tc(Xd, Yd, [None, rows1, rows2])
+    finally:
+        eng.TC_CELLS = old
+    assert torch.equal(G_sets, G_tc)
+
+
+def test_config3_full_width_properties():
+    """BASELINE configs[2] shape at full width: 2000 lagged columns (40 base signals x 50 shifts), 5 random folds,
+    T = 900k so that the largest cell of the fold partition (0.8^5 T = 295k rows) exceeds one int32-safe segment.
+    Checked with an independent fp64 implementation (torch matmuls on the explicit design)."""
+    T, P, F = 900_000, 40, 5
+    shifts = [0] + [s for s in range(-20, 30) if s != 0]
+    X0 = torch.from_numpy(synth_data.synth_base(T, P, 909)).cuda()
+    X = sglm_pp.timeshift_multiple(X0, shift_amt_list=shifts)[29:T - 20]
+    n, C = X.shape
+    assert C == 2000
+    beta = torch.from_numpy(synth_data.synth_kernels(P, shifts, 909)).cuda()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    s = X @ beta
+    y = s + float(s.std()) * 1.5 * torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+    y = (y - y.mean()) / y.std()
+    cv_idx = synth_data.synth_folds(n, F, 909, group=1000)
+    alphas = np.logspace(-4, 0, 5)
+    grid = [dict(alpha=float(a), l1_ratio=float(l), max_iter=1000, fit_intercept=True, tol=1e-4)
+            for l in (0.1, 0.9) for a in alphas]
+    res = sglm_cv.cv_glm_mult_params(X, y, cv_idx, "Gaussian", [dict(k) for k in grid], score_method="r2")
+    plan = dict(nat.last_tc_plan)
+    assert plan["cells"] and plan["n_aug"] == C + 2
+    full = res["full_cv_results"]
+    scores = [r["cv_R2_score"] for r in full]
+    assert res["best_score"] == max(scores) and res["best_params"] == full[int(np.argmax(scores))]["glm_kwargs"]
+    # heaviest and lightest models by coordinate updates
+    work = sorted(range(len(full)), key=lambda k: -float(full[k]["_fit_info"]["cd_info"][:, 3].sum()))
+    picked = work[:3] + work[-3:]
+    xbar = X.mean(0)
+    ybar = y.mean()
+    yc = y - ybar
+    yy = float(yc @ yc)
+    for k in picked:
+        r = full[k]
+        kw = r["glm_kwargs"]
+        # the refit on all rows
+        w = torch.from_numpy(r["model"].coef_).cuda()
+        resid = yc - (X @ w - xbar @ w)
+        l1 = kw["alpha"] * kw["l1_ratio"] * n
+        l2 = kw["alpha"] * (1 - kw["l1_ratio"]) * n
+        xta = X.T @ resid - xbar * resid.sum() - l2 * w
+        dn = float(xta.abs().max())
+        R2, ww = float(resid @ resid), float(w @ w)
+        scale = min(1.0, l1 / dn) if dn > 0 else 1.0
+        gap = 0.5 * (R2 + l2 * ww) + l1 * float(w.abs().sum()) - (-0.5 * scale ** 2 * (R2 + l2 * ww) + scale * float(resid @ yc))
+        status = int(r["_fit_info"]["status"][F])
+        if status == 0:                                             # converged: sklearn's stopping rule holds
+            assert gap <= 1e-4 * yy * (1 + 1e-6), (kw, gap, 1e-4 * yy)
+        assert abs(gap - r["model"].model.dual_gap_) <= 1e-6 * yy      # the gap the kernel reports is the true gap
+        # KKT: |x_j'r - l2 w_j| <= l1 (+ slack of the gap) where w_j == 0
+        zero = w == 0
+        if status == 0 and bool(zero.any()):
+            assert float(xta[zero].abs().max()) <= l1 * 1.05 + 1e-6 * dn
+        b = float(ybar - xbar @ w)
+        assert abs(b - r["model"].intercept_) < 1e-9
+        # fold scores from the statistics == explicit pass over the rows of the fold
+        for f in (0, F - 1):
+            tr, te = cv_idx[f]
+            wf = torch.from_numpy(np.ascontiguousarray(r["cv_coefs"][:, f])).cuda()
+            for idx, key in ((te, "cv_scores_test"), (tr, "cv_scores_train")):
+                it = torch.from_numpy(idx).cuda()
+                Xi, yi = X[it], y[it]
+                pred = Xi @ wf + r["cv_intercepts"][f]
+                r2 = 1.0 - float(((yi - pred) ** 2).sum() / ((yi - yi.mean()) ** 2).sum())
+                assert abs(r2 - r[key][f]) < 1e-8, (kw, f, key, r2, r[key][f])
+                del Xi
+
+
+def _mini_frame(T, seed, with_nans):
+    rng = np.random.default_rng(seed)
+    df = pd.DataFrame({
+        "ev1": (rng.random(T) < 0.05).astype(float), "ev2": (rng.random(T) < 0.03).astype(float),
+        "sig": rng.standard_normal(T), "trial": (np.arange(T) // 50).astype(float),
+    })
+    df["resp"] = 0.8 * df["ev1"].shift(2).fillna(0) - 0.5 * df["ev2"].shift(-1).fillna(0) + 0.3 * df["sig"] + 0.5 * rng.standard_normal(T)
+    if with_nans:
+        df.loc[[17, 18, 400, 1203], "sig"] = np.nan
+        df.loc[[950], "ev1"] = np.nan
+    return df
+
+
+@pytest.mark.parametrize("with_nans", [False, True])
+def test_device_design_matches_host_path(with_nans):
+    """timeshift_cols(device=True) -> dropna -> column selection -> simple_cv_fit equals the reference-typed host
+    path (DataFrame out, pandas dropna) value for value; materialising the DeviceDesign gives the same bits."""
+    T = 3000
+    df = _mini_frame(T, 3, with_nans)
+    cols = ["ev1", "ev2", "sig"]
+    host = sglm_ez.timeshift_cols(df, cols, neg_order=-4, pos_order=6)
+    dev = sglm_ez.timeshift_cols(df, cols, neg_order=-4, pos_order=6, device=True)
+    assert isinstance(dev, sglm_pp.DeviceDesign) and list(dev.columns) == list(host.columns) and dev.shape == host.shape
+    assert np.asarray(dev).tobytes() == host.to_numpy(dtype=np.float64).tobytes()
+    host_c, dev_c = host.dropna(), dev.dropna()
+    assert dev_c.shape == host_c.shape
+    assert np.array_equal(np.asarray(dev_c.index), np.asarray(host_c.index))
+    if with_nans:
+        assert not isinstance(dev_c._rows, tuple)                      # the row-list gather ran
+    assert np.asarray(dev_c).tobytes() == host_c.to_numpy(dtype=np.float64).tobytes()
+    x_cols = [c for c in host.columns if c not in ("resp", "trial")]
+    assert np.asarray(dev_c[x_cols]).tobytes() == host_c[x_cols].to_numpy(dtype=np.float64).tobytes()
+    np.random.seed(0)
+    cv_idx = sglm_ez.cv_idx_by_timeframe(host_c, timesteps_per_bucket=50, num_folds=3, test_size=0.25)
+    grid = sglm_cv.generate_mult_params({"alpha": [0.0, 0.01, 0.1], "l1_ratio": [0.0, 0.5]},
+                                        {"max_iter": 1000, "fit_intercept": True})
+    a = sglm_ez.simple_cv_fit(host_c[x_cols], host_c["resp"], cv_idx, [dict(k) for k in grid], score_method="r2")
+    b = sglm_ez.simple_cv_fit(dev_c[x_cols], dev_c["resp"], cv_idx, [dict(k) for k in grid], score_method="r2")
+    assert a[2] == b[2] and a[0] == b[0]
+    for ra, rb in zip(a[4]["full_cv_results"], b[4]["full_cv_results"]):
+        assert np.array_equal(ra["cv_coefs"], rb["cv_coefs"]) and np.array_equal(ra["cv_scores_test"], rb["cv_scores_test"])
+    # ... and both equal the oracle's grid on the host arrays
+    want = orc.cv_glm_mult_params(host_c[x_cols].values, host_c["resp"].values, cv_idx, "Normal", [dict(k) for k in grid],
+                                  score_method="r2")
+    assert want["best_params"] == b[2]
+    for rw, rb in zip(want["full_cv_results"], b[4]["full_cv_results"]):
+        assert coef_rel_err(rb["model"].coef_, rw["model"].coef_) < 1e-4
+        assert np.allclose(rb["cv_scores_test"], rw["cv_scores_test"], atol=1e-6)
+
+
+def test_fused_dropna_at_scale_contiguous_and_row_list():
+    """500k x (12 x 21) lag design on the device: dropna of the NaN edge rows is a view of one gather; NaNs inside
+    the base signals switch to the row-list gather; both equal the explicit design with the NaN rows removed."""
+    T, P = 500_000, 12
+    X0 = synth_data.synth_base(T, P, 11)
+    shifts = [0] + list(range(-10, 0)) + list(range(1, 11))
+    d = sglm_pp.timeshift_multiple(X0, shift_amt_list=shifts, device=True)
+    full = d.tensor()
+    keep = ~torch.isnan(full).any(dim=1)
+    dc = d.dropna()
+    assert isinstance(dc._rows, tuple) and dc._rows == (10, T - 10)
+    assert torch.equal(dc.tensor(), full[keep])
+    X0n = X0.copy()
+    bad = np.random.default_rng(1).choice(T, 300, replace=False)
+    X0n[bad, np.random.default_rng(2).integers(0, P, 300)] = np.nan
+    dn = sglm_pp.timeshift_multiple(X0n, shift_amt_list=shifts, device=True)
+    fulln = dn.tensor()
+    keepn = ~torch.isnan(fulln).any(dim=1)
+    dnc = dn.dropna()
+    assert dnc.shape[0] == int(keepn.sum()) and not isinstance(dnc._rows, tuple)
+    assert torch.equal(dnc._rows, torch.nonzero(keepn).reshape(-1))
+    assert torch.equal(dnc.tensor(), fulln[keepn])
+
+
+def test_multi_session_batch_equals_per_session_calls():
+    """BASELINE configs[4] shape (independent sessions, the same ElasticNet grid) at reduced size: the batched plan
+    (one coordinate-descent launch over the models of all sessions) returns exactly what per-session calls return."""
+    P, h = 24, 20
+    shifts = [0] + [s for s in range(-20, 30) if s != 0]
+    sessions = []
+    for sidx in range(3):
+        T = 6000 + 500 * sidx
+        X0 = synth_data.synth_base(T, P, 500 + sidx)
+        Xd = orc.timeshift_multiple(X0, shift_amt_list=shifts)
+        Xd = Xd[~np.isnan(Xd).any(axis=1)]
+        y = synth_data.synth_response(Xd, synth_data.synth_kernels(P, shifts, 500 + sidx), 500 + sidx)
+        sessions.append((Xd, y, synth_data.synth_folds(Xd.shape[0], 3, 500 + sidx, group=250)))
+    grid = [dict(alpha=float(a), l1_ratio=float(l), max_iter=1000, fit_intercept=True, tol=1e-4)
+            for l in (0.2, 0.9) for a in np.logspace(-3, -0.5, 4)]
+    batched = sglm_cv.cv_glm_mult_params_sessions(sessions, "Gaussian", [dict(k) for k in grid], score_method="r2")
+    assert len(batched) == 3
+    for (X, y, cv), got in zip(sessions, batched):
+        want = sglm_cv.cv_glm_mult_params(X, y, cv, "Gaussian", [dict(k) for k in grid], score_method="r2")
+        assert got["best_params"] == want["best_params"] and got["best_score"] == want["best_score"]
+        for a, b in zip(got["full_cv_results"], want["full_cv_results"]):
+            assert np.array_equal(a["cv_coefs"], b["cv_coefs"])
+            assert np.array_equal(a["model"].coef_, b["model"].coef_)
+            assert np.array_equal(a["cv_scores_test"], b["cv_scores_test"])
+            assert a["model"].model.n_iter_ == b["model"].model.n_iter_
+    ref = orc.cv_glm_mult_params(sessions[0][0], sessions[0][1], sessions[0][2], "Gaussian", [dict(k) for k in grid],
+                                 score_method="r2", engine="sklearn")
+    assert ref["best_params"] == batched[0]["best_params"]
+    for a, b in zip(batched[0]["full_cv_results"], ref["full_cv_results"]):
+        assert coef_rel_err(a["model"].coef_, b["model"].coef_) < 1e-4
+        assert a["model"].model.n_iter_ == b["model"].model.n_iter_
+
+
+def test_cv_idx_validation_matches_numpy_semantics():
+    """Boolean masks select rows, negative positions wrap, out-of-range positions raise IndexError."""
+    rng = np.random.default_rng(4)
+    n, C = 400, 6
+    X = rng.standard_normal((n, C))
+    y = X @ rng.standard_normal(C) + 0.1 * rng.standard_normal(n)
+    te = np.arange(0, n, 4)
+    tr = np.setdiff1d(np.arange(n), te)
+    kw = dict(alpha=0.01, l1_ratio=0.5, max_iter=1000)
+    a = sglm_cv.cv_glm_single_params(X, y, [(tr, te)], "Gaussian", dict(kw), resp_list=[], score_method="r2")
+    m_te = np.zeros(n, dtype=bool); m_te[te] = True
+    b = sglm_cv.cv_glm_single_params(X, y, [(~m_te, m_te)], "Gaussian", dict(kw), resp_list=[], score_method="r2")
+    c = sglm_cv.cv_glm_single_params(X, y, [(tr - n, te - n)], "Gaussian", dict(kw), resp_list=[], score_method="r2")
+    for other in (b, c):
+        assert np.array_equal(a["cv_coefs"], other["cv_coefs"]) and np.array_equal(a["cv_scores_test"], other["cv_scores_test"])
+    with pytest.raises(IndexError):
+        sglm_cv.cv_glm_single_params(X, y, [(tr, np.array([0, n]))], "Gaussian", dict(kw), resp_list=[])
+    with pytest.raises(IndexError):
+        sglm_cv.cv_glm_single_params(X, y, [(torch.from_numpy(tr).cuda(), torch.tensor([0, n + 3]).cuda())], "Gaussian",
+                                     dict(kw), resp_list=[])
+
+
+def test_more_than_64_row_sets():
+    """One fold per bucket (cv_idx_from_bucket_ids(num_folds=None)) gives > 64 row sets on the fp64 path."""
+    rng = np.random.default_rng(9)
+    n, C, F = 1400, 5, 70
+    X = rng.standard_normal((n, C))
+    y = X @ rng.standard_normal(C) + 0.2 * rng.standard_normal(n)
+    groups = np.arange(n) // (n // F)
+    cv_idx = [(np.flatnonzero(groups != f), np.flatnonzero(groups == f)) for f in range(F)]
+    kw = dict(alpha=0.0, l1_ratio=0.0, max_iter=10)
+    got = sglm_cv.cv_glm_single_params(X, y, cv_idx, "Gaussian", dict(kw), resp_list=[], score_method="r2")
+    want = orc.cv_glm_single_params(X, y, cv_idx, "Gaussian", dict(kw), score_method="r2")
+    assert got["cv_coefs"].shape == (C, F)
+    assert np.allclose(got["cv_coefs"], want["cv_coefs"], rtol=1e-7, atol=1e-10)
+    assert np.allclose(got["cv_scores_test"], want["cv_scores_test"], atol=1e-6)
