@@ -248,13 +248,23 @@ int sglm_enet_cd_cluster_f64(const double *const *prob_Q, const double *const *p
  * _ridge._solve_cholesky (sklearn/linear_model/_ridge.py:215-227) and the
  * full-rank case of LinearRegression (_base.py:700-756):
  *   (Qc + alpha[k] I) w_k = qc   for k < n_alpha, one CTA per alpha.
- * work holds n_alpha * (C+1) * ldq doubles.  status[k] = 0 ok, 1 = not positive
- * definite (pivot <= 0).
+ * work holds n_alpha * (C+1) * ldq doubles.  status[k]: bit 0 = not positive definite
+ * (a pivot <= 0), bit 1 = a pivot at rounding-noise level (<= 1e-11 of the largest diagonal
+ * entry: numerically rank deficient; the solve still completes).
  * ------------------------------------------------------------------------- */
 size_t sglm_ridge_workspace_bytes(int32_t C, int64_t ldq, int32_t n_alpha);
 int sglm_ridge_solve_f64(const double *Qc, int64_t ldq, const double *qc, int32_t C,
                          const double *alpha, int32_t n_alpha, double *W, int64_t ldw,
                          int32_t *status, void *work, size_t work_bytes, void *stream);
+/* (a8) minimum-norm least squares for numerically rank-deficient normal equations — what scipy.linalg.lstsq(X, y,
+ * cond = rcond) returns inside sklearn's LinearRegression (_base.py:750-753; reached from backend/sglm.py:96-101 when
+ * alpha == 0): singular values of the centred X below rcond * s_max are dropped.  One-sided Jacobi on Qc = Xc'Xc, on
+ * the device.  Runs only when (*status & status_mask) != 0 (*status: device int32 from sglm_ridge_solve_f64), overwrites
+ * w and clears *status; returns at once otherwise — no host synchronisation either way.  shift = alpha > 0 solves the
+ * Ridge system (Qc + alpha I) w = qc the same way (sklearn's SVD fallback for a failed Cholesky, _ridge.py:_solve_svd). */
+size_t sglm_ols_minnorm_workspace_bytes(int32_t C);
+int sglm_ols_minnorm_f64(const double *Qc, int64_t ldq, const double *qc, int32_t C, double rcond, double shift,
+                         int32_t status_mask, int32_t *status, double *w, void *work, size_t work_bytes, void *stream);
 /* x = (L L')^-1 rhs with the Cholesky factor of system k that sglm_ridge_solve_f64 left in `work`
  * (a solve without a second factorisation: chord iterations of the Poisson Newton solver). */
 int sglm_chol_solve_f64(const void *work, int64_t ldq, int32_t C, int32_t k, const double *rhs, double *out,

@@ -606,48 +606,47 @@ def solve_models(models, C, do_screening=True):
         if m.kind in ("ridge", "ols"):
             groups.setdefault(id(m.problem), []).append(i)
     # one Cholesky launch per problem (one CTA per alpha): the launches of the problems of a grid are independent
-    # and each fills only a few SMs, so they go to separate streams and run side by side
+    # and each fills only a few SMs, so they go to separate streams and run side by side.  Systems whose pivots
+    # fell to rounding-noise level (rank-deficient least squares) or below zero are re-solved by the minimum-norm
+    # solver on the same stream — decided on the device, no read-back (sglm_ols_minnorm_f64).
     launched = []
     if groups:
         main = torch.cuda.current_stream()
         ready = torch.cuda.Event()
         ready.record(main)
+        mn_bytes = nat.lib().sglm_ols_minnorm_workspace_bytes(C)
     for gi, idxs in enumerate(groups.values()):
         p = models[idxs[0]].problem
         n_a = len(idxs)
         wb = nat.lib().sglm_ridge_workspace_bytes(C, p.ldq, n_a)
+        # buffers are allocated on the main stream (their allocator pool) and handed to the side stream
+        alphas = _dev([0.0 if models[i].kind == "ols" else models[i].alpha for i in idxs], np.float64)
+        work = torch.empty(wb // 8, dtype=torch.float64, device="cuda")
+        Wr = _empty((n_a, ldw))
+        st = torch.empty(n_a, dtype=torch.int32, device="cuda")
+        mn_work = torch.empty(mn_bytes // 8, dtype=torch.float64, device="cuda")
         st_ = main if gi == 0 else _side_stream(100 + gi % 8)
         if st_ is not main:
             st_.wait_event(ready)
         with torch.cuda.stream(st_):
-            alphas = _dev([0.0 if models[i].kind == "ols" else models[i].alpha for i in idxs], np.float64)
-            work = torch.empty(wb // 8, dtype=torch.float64, device="cuda")
-            Wr = _empty((n_a, ldw))
-            st = torch.empty(n_a, dtype=torch.int32, device="cuda")
             call("sglm_ridge_solve_f64", ptr(p.Qc), p.ldq, ptr(p.qc), C, ptr(alphas), n_a, ptr(Wr), ldw, ptr(st),
                  ptr(work), wb, stream_ptr())
+            for k, i in enumerate(idxs):
+                ols = models[i].kind == "ols"
+                call("sglm_ols_minnorm_f64", ptr(p.Qc), p.ldq, ptr(p.qc), C, float(models[i].tol) if ols else 0.0,
+                     0.0 if ols else float(models[i].alpha), 3 if ols else 1, ctypes.c_void_p(st.data_ptr() + 4 * k),
+                     ptr(Wr[k]), ptr(mn_work), mn_bytes, stream_ptr())
             if st_ is not main:
                 ev = torch.cuda.Event()
                 ev.record(st_)
                 main.wait_event(ev)
-                for t in (alphas, work, Wr, st):
+                for t in (alphas, work, Wr, st, mn_work):
                     t.record_stream(st_)
-        launched.append((idxs, p, Wr, st, work, alphas))
-    for idxs, p, Wr, st, work, alphas in launched:
-        st_h = st.cpu().numpy()
-        for k, i in enumerate(idxs):
-            if st_h[k] != 0 and models[i].kind == "ols":
-                # rank-deficient least squares: minimum-norm solution, singular values below
-                # 1e-6 * s_max dropped — what scipy.linalg.lstsq(cond=1e-6) returns for
-                # LinearRegression (sklearn _base.py:750-753).  Rare path; dense symmetric
-                # eigensolver from the CUDA libraries, still on the device.
-                lam, Vec = torch.linalg.eigh(p.Qc[:, :C])
-                keep = lam > (1e-6 ** 2) * lam.max().clamp_min(0.0)
-                inv = torch.where(keep, 1.0 / torch.where(keep, lam, torch.ones_like(lam)), torch.zeros_like(lam))
-                Wr[k, :C] = Vec @ (inv * (Vec.T @ p.qc))
-                st_h[k] = 0
+        launched.append((idxs, Wr, st))
+    for idxs, Wr, st in launched:
         W.index_copy_(0, _dev(idxs, np.int64), Wr)
-        status[idxs] = st_h * 2                                        # 2 = not positive definite
+        # bit 1 alone (a tiny but positive pivot of a Ridge system) is not an error; bit 0 is cleared by the fallback
+        status[idxs] = (st.cpu().numpy() & 1) * 2                     # 2 = not positive definite and not recovered
     del launched
     return W, info, status
 

@@ -108,7 +108,7 @@ class LinearRegression(_Base):
             fit_intercept, copy_X, tol, n_jobs, positive
 
     def _spec(self, problem):
-        return eng.ModelSpec(problem, "ols")
+        return eng.ModelSpec(problem, "ols", tol=self.tol)      # tol = lstsq cond (_base.py:750-753)
 
 
 class Ridge(_Base):

@@ -62,6 +62,8 @@ _PROTOTYPES = {
     "sglm_ridge_workspace_bytes": (c_sz, [c_i32, c_i64, c_i32]),
     "sglm_ridge_solve_f64": (c_i32, [c_vp, c_i64, c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp, c_vp,
                                      c_sz, c_vp]),
+    "sglm_ols_minnorm_workspace_bytes": (c_sz, [c_i32]),
+    "sglm_ols_minnorm_f64": (c_i32, [c_vp, c_i64, c_vp, c_i32, c_f64, c_f64, c_i32, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "sglm_chol_solve_f64": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "sglm_finalize_models_f64": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp,
                                          c_vp, c_i64, c_vp]),

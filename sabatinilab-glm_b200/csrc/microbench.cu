@@ -15,11 +15,11 @@ probe_read_kernel(const double2 *__restrict__ buf, long long n2, int repeats, do
         for (; i + 7 * stride < n2; i += 8 * stride) {
             double2 v[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = __ldg(buf + i + k * stride);
+            for (int k = 0; k < 8; ++k) v[k] = __ldcg(buf + i + k * stride);      // L2 (no L1 allocation)
 #pragma unroll
             for (int k = 0; k < 8; ++k) acc += v[k].x + v[k].y;
         }
-        for (; i < n2; i += stride) { const double2 v = __ldg(buf + i); acc += v.x + v.y; }
+        for (; i < n2; i += stride) { const double2 v = __ldcg(buf + i); acc += v.x + v.y; }
     }
     if (acc == 1.2345678e300) sink[0] = acc;      // never true for finite data: keeps the loads alive
 }

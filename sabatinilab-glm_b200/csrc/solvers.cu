@@ -470,6 +470,19 @@ ridge_cholesky_kernel(const double *__restrict__ Qc, long long ldq, const double
     const double a = alpha[kq];
     double *M = work + (long long)kq * (C + 1) * ldq;
     if (tid == 0) bad = 0;
+    // pivots at rounding-noise level (relative to the largest diagonal entry) mark a numerically rank-deficient
+    // system: status bit 1 (the factorisation still completes); a non-positive pivot sets bit 0
+    __shared__ double s_dmax[RC_THREADS / 32];
+    {
+        double dm = 0.0;
+        for (int j = tid; j < C; j += RC_THREADS) dm = fmax(dm, fabs(Qc[(long long)j * ldq + j] + a));
+        dm = warp_max(dm);
+        if ((tid & 31) == 0) s_dmax[tid >> 5] = dm;
+    }
+    __syncthreads();
+    double tiny_pivot = 0.0;
+    for (int w_ = 0; w_ < RC_THREADS / 32; ++w_) tiny_pivot = fmax(tiny_pivot, s_dmax[w_]);
+    tiny_pivot *= 1e-11;
 
     // M = lower(Qc) + a I ; row C = qc'
     for (long long e = tid; e < (long long)(C + 1) * C; e += RC_THREADS) {
@@ -490,7 +503,8 @@ ridge_cholesky_kernel(const double *__restrict__ Qc, long long ldq, const double
         if (tid < 32) {
             for (int c = 0; c < nb; ++c) {
                 double d = D[c * 33 + c];
-                if (!(d > 0.0)) { if (tid == 0) bad = 1; d = nan(""); }
+                if (!(d > 0.0)) { if (tid == 0) bad |= 1; d = nan(""); }
+                else if (d <= tiny_pivot) { if (tid == 0) bad |= 2; }
                 const double l = sqrt(d);
                 __syncwarp();
                 if (tid == 0) D[c * 33 + c] = l;
@@ -633,6 +647,19 @@ ridge_cholesky_ll_kernel(const double *__restrict__ Qc, long long ldq, const dou
     const double a = alpha[kq];
     double *M = work + (long long)kq * (C + 1) * ldq;
     if (tid == 0) bad = 0;
+    // pivots at rounding-noise level (relative to the largest diagonal entry) mark a numerically rank-deficient
+    // system: status bit 1 (the factorisation still completes); a non-positive pivot sets bit 0
+    __shared__ double s_dmax[RC_THREADS / 32];
+    {
+        double dm = 0.0;
+        for (int j = tid; j < C; j += RC_THREADS) dm = fmax(dm, fabs(Qc[(long long)j * ldq + j] + a));
+        dm = warp_max(dm);
+        if ((tid & 31) == 0) s_dmax[tid >> 5] = dm;
+    }
+    __syncthreads();
+    double tiny_pivot = 0.0;
+    for (int w_ = 0; w_ < RC_THREADS / 32; ++w_) tiny_pivot = fmax(tiny_pivot, s_dmax[w_]);
+    tiny_pivot *= 1e-11;
     const int ty = tid >> 3, tx = tid & 7;      // rows ty + 32u (u < 8), columns tx + 8v (v < 4)
     const bool al16 = ((ldq & 1) == 0) && ((reinterpret_cast<uintptr_t>(M) & 15) == 0);
 
@@ -716,7 +743,8 @@ ridge_cholesky_ll_kernel(const double *__restrict__ Qc, long long ldq, const dou
         if (tid < 32) {
             for (int c = 0; c < nb; ++c) {
                 double d = D[c * 33 + c];
-                if (!(d > 0.0)) { if (tid == 0) bad = 1; d = nan(""); }
+                if (!(d > 0.0)) { if (tid == 0) bad |= 1; d = nan(""); }
+                else if (d <= tiny_pivot) { if (tid == 0) bad |= 2; }
                 const double l = sqrt(d);
                 __syncwarp();
                 if (tid == 0) D[c * 33 + c] = l;
