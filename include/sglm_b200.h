@@ -175,6 +175,31 @@ int sglm_gram_tc_cells_f64(const double *X, int64_t ldx, const double *Y, int64_
                            const int32_t *member_host, double *G, int64_t ldg, void *workspace,
                            size_t workspace_bytes, int32_t use_check_gemm, void *stream);
 
+/* Row-sharded form (one process per GPU, each holding a slice of the rows; SURVEY.md §8e "alternative"):
+ *   colstats / exponents : the column analysis in two steps — every rank scans its rows (colmax_bits = bits of
+ *              max |z| per column, col_lsb = lowest set bit per column), the ranks combine them (all-reduce max /
+ *              min), and sglm_gram_tc_exponents derives the same colE / colS everywhere (colS: lowest set bits on
+ *              entry, digit-plane counts on exit);
+ *   cells_partial : slicing + int8 GEMM + cell sums of THIS rank's rows; the int64 plane Grams of the n_out row sets
+ *              stay in the workspace at the offset sglm_gram_tc_cells_sgout reports (same offset and size on every
+ *              rank: the digit-plane layout depends only on the combined analysis); the caller adds them over the
+ *              ranks (ncclAllReduce int64 sum — exact, so the result has the bits of the one-GPU computation);
+ *   cells_combine : fp64 recombination of the summed plane Grams -> G. */
+int sglm_gram_tc_colstats_f64(const double *X, int64_t ldx, const double *Y, int64_t ldy, int32_t n_y, int64_t T,
+                              int32_t C, uint64_t *colmax_bits, int32_t *col_lsb, void *stream);
+int sglm_gram_tc_exponents(const uint64_t *colmax_bits, int32_t n_aug, int32_t max_planes, int32_t *colE,
+                           int32_t *colS, int32_t *flag, void *stream);
+int sglm_gram_tc_cells_sgout(int32_t n_aug, const int32_t *colS_host, int32_t n_cells, const int64_t *cell_rows_host,
+                             int32_t n_out, uint64_t *offset_bytes, uint64_t *size_bytes);
+int sglm_gram_tc_cells_partial_f64(const double *X, int64_t ldx, const double *Y, int64_t ldy, int32_t n_y, int64_t T,
+                                   int32_t C, const int32_t *colE, const int32_t *colS, const int32_t *colS_host,
+                                   int32_t n_cells, const int64_t *cell_rows_host, const int64_t *rows, int32_t n_out,
+                                   const int32_t *member_host, void *workspace, size_t workspace_bytes, void *stream);
+int sglm_gram_tc_cells_combine_f64(int32_t C, int32_t n_y, const int32_t *colE, const int32_t *colS,
+                                   const int32_t *colS_host, int32_t n_cells, const int64_t *cell_rows_host,
+                                   int32_t n_out, double *G, int64_t ldg, void *workspace, size_t workspace_bytes,
+                                   void *stream);
+
 /* Index lists -> per-row multiplicities: counts[idx[i]] += 1 (the fold row sets of
  * backend/sglm_cv.py:106-110, X[idx_train,:] / X[idx_test,:]).  counts must be zeroed. */
 int sglm_index_counts_f64(const int64_t *idx, int64_t n_idx, double *counts, int64_t T,

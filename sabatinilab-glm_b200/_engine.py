@@ -268,6 +268,74 @@ def suffstats_tc(Xd, Yd, set_rows, check_gemm=False):
     return G, colS_h
 
 
+def suffstats_tc_sharded(Xd, Yd, set_rows, all_reduce):
+    """Row-sharded tensor-core Gram: this process holds a SLICE of the rows (Xd, Yd, set_rows in local row
+    numbers); `all_reduce(tensor, op)` combines a CUDA tensor over the processes in place (op in "max", "min",
+    "sum").  Three small collectives: column maxima (int64 max) and lowest set bits (int32 min) so that every rank
+    cuts the same digit planes, then the int64 plane Grams of the row sets (sum — exact integer arithmetic, so the
+    result has the bits of the one-GPU computation).  Returns G [n_sets, n_aug, ldg], identical on every rank."""
+    torch = nat.require_cuda()
+    T, C = Xd.shape
+    n_y = Yd.shape[1]
+    n_aug = C + n_y + 1
+    n_sets = len(set_rows)
+    ldg = _round_up(n_aug, 8)
+    colmax = torch.empty(n_aug, dtype=torch.int64, device="cuda")
+    colS = torch.empty(n_aug, dtype=torch.int32, device="cuda")
+    colE = torch.empty(n_aug, dtype=torch.int32, device="cuda")
+    flag = torch.empty(1, dtype=torch.int32, device="cuda")
+    call("sglm_gram_tc_colstats_f64", ptr(Xd), row_stride(Xd), ptr(Yd), row_stride(Yd), n_y, T, C, ptr(colmax), ptr(colS),
+         stream_ptr())
+    all_reduce(colmax, "max")            # bits of non-negative doubles order like integers; the NaN pattern wins
+    all_reduce(colS, "min")
+    call("sglm_gram_tc_exponents", ptr(colmax), n_aug, 8, ptr(colE), ptr(colS), ptr(flag), stream_ptr())
+    host = torch.cat([colS, flag]).cpu().numpy()
+    if host[-1] != 0:
+        raise ValueError("Input contains NaN, infinity or a value too large for dtype('float64').")
+    colS_h = np.ascontiguousarray(host[:-1], dtype=np.int32)
+    cells = _row_cells(set_rows, T)
+    if cells is None:                    # no overlap among this rank's rows: every set is its own cell
+        lists = [torch.arange(T, dtype=torch.int64, device="cuda") if r is None else r.to(torch.int64) for r in set_rows]
+        member = np.eye(n_sets, dtype=np.int32)
+    else:
+        lists, member = cells
+    n_lists = len(lists)
+    sizes = np.ascontiguousarray([int(r.numel()) for r in lists], dtype=np.int64)
+    parts = []
+    for body, n in zip(lists, sizes):
+        parts.append(body)
+        pad = (-int(n)) % 128
+        if pad:
+            parts.append(torch.full((pad,), -1, dtype=torch.int64, device="cuda"))
+    rows = torch.cat(parts) if parts else torch.empty(0, dtype=torch.int64, device="cuda")
+    if rows.numel() == 0:
+        rows = torch.full((128,), -1, dtype=torch.int64, device="cuda")
+    colS_p, sizes_p = colS_h.ctypes.data_as(ctypes.c_void_p), sizes.ctypes.data_as(ctypes.c_void_p)
+    ws_bytes = nat.lib().sglm_gram_tc_cells_workspace_bytes(n_aug, colS_p, n_lists, sizes_p, n_sets)
+    if ws_bytes == 0:
+        raise nat.SglmNativeError("gram_tc: invalid plan")
+    off_b, size_b = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    if nat.lib().sglm_gram_tc_cells_sgout(n_aug, colS_p, n_lists, sizes_p, n_sets, ctypes.byref(off_b), ctypes.byref(size_b)) != 0:
+        raise nat.SglmNativeError("gram_tc: " + nat.lib().sglm_last_error().decode())
+    info = np.zeros(4, dtype=np.int64)
+    nat.lib().sglm_gram_tc_plan_info(n_aug, colS_p, n_lists, sizes_p, info.ctypes.data_as(ctypes.c_void_p))
+    nat.last_tc_plan = dict(S=int(info[0]), n_pos=int(info[1]), tiles=int(info[2]), k_parts=int(info[3]),
+                            planes=int(colS_h.sum()), n_aug=n_aug, row_lists=n_lists, cells=cells is not None, sharded=True)
+    raw = torch.empty(ws_bytes + 1024, dtype=torch.uint8, device="cuda")
+    off = (-raw.data_ptr()) % 1024
+    ws_p = ctypes.c_void_p(raw.data_ptr() + off)
+    member = np.ascontiguousarray(member, dtype=np.int32)
+    call("sglm_gram_tc_cells_partial_f64", ptr(Xd), row_stride(Xd), ptr(Yd), row_stride(Yd), n_y, T, C, ptr(colE),
+         ptr(colS), colS_p, n_lists, sizes_p, ptr(rows), n_sets, member.ctypes.data_as(ctypes.c_void_p), ws_p, ws_bytes,
+         stream_ptr())
+    sg = raw[off + off_b.value: off + off_b.value + size_b.value].view(torch.int64)
+    all_reduce(sg, "sum")
+    G = _zeros((n_sets, n_aug, ldg))
+    call("sglm_gram_tc_cells_combine_f64", C, n_y, ptr(colE), ptr(colS), colS_p, n_lists, sizes_p, n_sets, ptr(G), ldg,
+         ws_p, ws_bytes, stream_ptr())
+    return G
+
+
 TC_CELLS = None      # False: one GEMM pass per row set (no cell decomposition); None: decompose when it pays
 _MAX_CELLS = 64
 

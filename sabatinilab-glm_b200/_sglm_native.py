@@ -48,6 +48,13 @@ _PROTOTYPES = {
     "sglm_gram_tc_cells_workspace_bytes": (c_sz, [c_i32, c_vp, c_i32, c_vp, c_i32]),
     "sglm_gram_tc_cells_f64": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp,
                                        c_vp, c_i32, c_vp, c_vp, c_i64, c_vp, c_sz, c_i32, c_vp]),
+    "sglm_gram_tc_colstats_f64": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp]),
+    "sglm_gram_tc_exponents": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "sglm_gram_tc_cells_sgout": (c_i32, [c_i32, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp]),
+    "sglm_gram_tc_cells_partial_f64": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp, c_i32,
+                                               c_vp, c_vp, c_i32, c_vp, c_vp, c_sz, c_vp]),
+    "sglm_gram_tc_cells_combine_f64": (c_i32, [c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp,
+                                               c_sz, c_vp]),
     "sglm_index_counts_f64": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp]),
     "sglm_center_stats_f64": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_i64,
                                       c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -130,7 +137,7 @@ def ptr(t):
 
 
 # kernels launched per ABI call (for the launch count bench.py reports)
-_KERNELS_PER_CALL = {"sglm_suffstats_f64": 3, "sglm_gram_tc_analyze_f64": 3, "sglm_gram_tc_f64": 3, "sglm_gram_tc_cells_f64": 4, "sglm_gram_tc_scaled_f64": 3, "sglm_gram_tc_analyze_scaled_f64": 2, "sglm_xt_vec_f64": 2, "sglm_score_f64": 2, "sglm_poisson_irls_prepare_f64": 2,
+_KERNELS_PER_CALL = {"sglm_suffstats_f64": 3, "sglm_gram_tc_analyze_f64": 3, "sglm_gram_tc_f64": 3, "sglm_gram_tc_cells_f64": 4, "sglm_gram_tc_cells_partial_f64": 3, "sglm_gram_tc_scaled_f64": 3, "sglm_gram_tc_analyze_scaled_f64": 2, "sglm_xt_vec_f64": 2, "sglm_score_f64": 2, "sglm_poisson_irls_prepare_f64": 2,
                      "sglm_timeshift_f64": 2}
 _timing = None         # when enabled: list of (name, start_event, end_event) on the current stream
 

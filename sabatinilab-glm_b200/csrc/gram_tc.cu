@@ -727,6 +727,40 @@ extern "C" int sglm_gram_tc_analyze_f64(const double *X, int64_t ldx, const doub
     return gram_tc_analyze(X, ldx, Y, ldy, n_y, T, C, nullptr, TC_SMAX, colE, colS, colmax_scratch, flag, stream);
 }
 
+// The analysis in two steps, for designs whose ROWS are spread over several GPUs: every rank runs the column pass
+// over its rows (colmax_bits = bits of max |z| per column, col_lsb = lowest set bit per column), the ranks combine
+// them (max / min: an all-reduce of 2 * n_aug integers), and every rank derives the same exponents and digit-plane
+// counts — so the integer digit planes, and the int64 plane Grams that are then summed over the ranks, are those of
+// the one-GPU computation bit for bit.
+extern "C" int sglm_gram_tc_colstats_f64(const double *X, int64_t ldx, const double *Y, int64_t ldy, int32_t n_y,
+                                         int64_t T, int32_t C, uint64_t *colmax_bits, int32_t *col_lsb, void *stream) {
+    SGLM_CHECK_ARG(T >= 0 && C >= 0 && n_y >= 0 && ldx >= C && ldy >= n_y, SGLM_E_SHAPE, "gram_tc_colstats: bad shape");
+    SGLM_CHECK_ARG(colmax_bits && col_lsb, SGLM_E_INVALID_ARG, "gram_tc_colstats: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_aug = C + n_y + 1;
+    SGLM_CUDA_OK(cudaMemsetAsync(colmax_bits, 0, (size_t)n_aug * sizeof(uint64_t), st));
+    SGLM_CUDA_OK(cudaMemsetAsync(col_lsb, 0x7f, (size_t)n_aug * sizeof(int), st));
+    if (T > 0) {
+        const int gy = (int)std::max<long long>(1, std::min<long long>(T / 256, 64LL * sm_count() / std::max(1, ceil_div(n_aug, 256))));
+        dim3 grid(ceil_div(n_aug, 256), gy);
+        tc_colmax_kernel<<<grid, 256, 0, st>>>(X, ldx, Y, ldy, C, n_y, T, nullptr, (unsigned long long *)colmax_bits, col_lsb);
+        SGLM_LAUNCH_OK("tc_colmax_kernel");
+    }
+    return SGLM_OK;
+}
+
+// colS holds the (combined) lowest set bits on entry and the digit-plane counts on exit.
+extern "C" int sglm_gram_tc_exponents(const uint64_t *colmax_bits, int32_t n_aug, int32_t max_planes, int32_t *colE,
+                                      int32_t *colS, int32_t *flag, void *stream) {
+    SGLM_CHECK_ARG(colmax_bits && colE && colS && flag && n_aug > 0, SGLM_E_INVALID_ARG, "gram_tc_exponents: bad argument");
+    SGLM_CHECK_ARG(max_planes >= 1 && max_planes <= TC_SMAX, SGLM_E_INVALID_ARG, "gram_tc_exponents: max_planes out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    SGLM_CUDA_OK(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    tc_exponent_kernel<<<ceil_div(n_aug, 256), 256, 0, st>>>((const unsigned long long *)colmax_bits, n_aug, max_planes, colE, colS, flag);
+    SGLM_LAUNCH_OK("tc_exponent_kernel");
+    return SGLM_OK;
+}
+
 // Weighted form: every row t of Z = [X | Y | 1] is scaled by row_scale[t] (= sqrt of a row weight, so that the
 // Gram is Z' diag(w) Z), and at most max_planes (1..8) digit planes are kept per column: with fewer planes than
 // a column needs its digits are rounded at the last plane (relative error 2^-(7 max_planes)) — the approximate
@@ -777,7 +811,7 @@ static int gram_tc_run(const double *X, int64_t ldx, const double *Y, int64_t ld
                        int32_t C, const int32_t *colE, const int32_t *colS, const int32_t *colS_host,
                        int32_t n_sets, const int64_t *set_rows_host, const int64_t *rows, int32_t n_out,
                        const int32_t *member_host, double *G, int64_t ldg, void *workspace, size_t workspace_bytes,
-                       int32_t use_check_gemm, void *stream, const double *rs = nullptr);
+                       int32_t use_check_gemm, void *stream, const double *rs = nullptr, int stage = 0);
 
 extern "C" int sglm_gram_tc_f64(const double *X, int64_t ldx, const double *Y, int64_t ldy, int32_t n_y, int64_t T,
                                 int32_t C, const int32_t *colE, const int32_t *colS, const int32_t *colS_host,
@@ -820,11 +854,52 @@ extern "C" int sglm_gram_tc_cells_f64(const double *X, int64_t ldx, const double
                        member_host, G, ldg, workspace, workspace_bytes, use_check_gemm, stream);
 }
 
+// Row-sharded form of sglm_gram_tc_cells_f64 (one process per GPU, each holding a slice of the rows):
+//   partial : slicing + int8 GEMM + cell sums of THIS rank's rows; leaves the int64 plane Grams of the n_out row
+//             sets at sglm_gram_tc_cells_sgout(...) inside the workspace (offset / byte count are the same on every
+//             rank because the digit-plane layout depends only on the combined column analysis);
+//   the caller adds them over the ranks (ncclAllReduce, int64 sum: exact, so the bits equal the one-GPU result);
+//   combine : fp64 recombination of the summed plane Grams -> G.
+extern "C" int sglm_gram_tc_cells_sgout(int32_t n_aug, const int32_t *colS_host, int32_t n_cells,
+                                        const int64_t *cell_rows_host, int32_t n_out, uint64_t *offset_bytes,
+                                        uint64_t *size_bytes) {
+    SGLM_CHECK_ARG(n_aug > 0 && n_cells > 0 && n_out > 0 && colS_host && cell_rows_host && offset_bytes && size_bytes,
+                   SGLM_E_INVALID_ARG, "gram_tc_cells_sgout: bad argument");
+    TcPlan p;
+    tc_make_plan(n_aug, colS_host, n_cells, (const long long *)cell_rows_host, p);
+    const TcLayout L = tc_layout(p, n_out);
+    *offset_bytes = L.off_sgout;
+    *size_bytes = (uint64_t)n_out * p.S * p.S * sizeof(long long);
+    return SGLM_OK;
+}
+
+extern "C" int sglm_gram_tc_cells_partial_f64(const double *X, int64_t ldx, const double *Y, int64_t ldy, int32_t n_y,
+                                              int64_t T, int32_t C, const int32_t *colE, const int32_t *colS,
+                                              const int32_t *colS_host, int32_t n_cells, const int64_t *cell_rows_host,
+                                              const int64_t *rows, int32_t n_out, const int32_t *member_host,
+                                              void *workspace, size_t workspace_bytes, void *stream) {
+    SGLM_CHECK_ARG(n_out >= 1 && member_host, SGLM_E_INVALID_ARG, "gram_tc_cells_partial: membership table missing");
+    SGLM_CHECK_ARG(n_cells <= TC_SUM_CELLS, SGLM_E_UNSUPPORTED, "gram_tc_cells_partial: at most %d cells", TC_SUM_CELLS);
+    double dummy;
+    return gram_tc_run(X, ldx, Y, ldy, n_y, T, C, colE, colS, colS_host, n_cells, cell_rows_host, rows, n_out,
+                       member_host, &dummy, C + n_y + 1, workspace, workspace_bytes, 0, stream, nullptr, 1);
+}
+
+extern "C" int sglm_gram_tc_cells_combine_f64(int32_t C, int32_t n_y, const int32_t *colE, const int32_t *colS,
+                                              const int32_t *colS_host, int32_t n_cells, const int64_t *cell_rows_host,
+                                              int32_t n_out, double *G, int64_t ldg, void *workspace,
+                                              size_t workspace_bytes, void *stream) {
+    SGLM_CHECK_ARG(n_out >= 1, SGLM_E_INVALID_ARG, "gram_tc_cells_combine: n_out");
+    static const int64_t no_rows = 0;
+    return gram_tc_run(nullptr, C, nullptr, n_y, n_y, 0, C, colE, colS, colS_host, n_cells, cell_rows_host, &no_rows,
+                       n_out, nullptr, G, ldg, workspace, workspace_bytes, 0, stream, nullptr, 2);
+}
+
 static int gram_tc_run(const double *X, int64_t ldx, const double *Y, int64_t ldy, int32_t n_y, int64_t T,
                        int32_t C, const int32_t *colE, const int32_t *colS, const int32_t *colS_host,
                        int32_t n_sets, const int64_t *set_rows_host, const int64_t *rows, int32_t n_out,
                        const int32_t *member_host, double *G, int64_t ldg, void *workspace, size_t workspace_bytes,
-                       int32_t use_check_gemm, void *stream, const double *rs) {
+                       int32_t use_check_gemm, void *stream, const double *rs, int stage) {
     const int n_aug = C + n_y + 1;
     SGLM_CHECK_ARG(T >= 0 && C >= 0 && n_y >= 0 && n_sets >= 1 && ldx >= C && ldy >= n_y && ldg >= n_aug, SGLM_E_SHAPE,
                    "gram_tc: bad shape");
@@ -846,7 +921,7 @@ static int gram_tc_run(const double *X, int64_t ldx, const double *Y, int64_t ld
     TcSeg *d_segs = (TcSeg *)(ws + L.off_segs);
     // the slicing pass writes every position of every real digit-plane row; only the padding rows
     // between levels have to be cleared
-    {
+    if (stage != 2) {
         long long covered = 0;
         for (int k = 1; k <= TC_SMAX; ++k) {
             const long long lo = (long long)p.level_off[k] + p.level_cnt[k];
@@ -856,12 +931,25 @@ static int gram_tc_run(const double *X, int64_t ldx, const double *Y, int64_t ld
         }
         if (p.S > covered) SGLM_CUDA_OK(cudaMemsetAsync(At + covered * p.n_pos, 0, (size_t)(p.S - covered) * p.n_pos, st));
     }
-    SGLM_CUDA_OK(cudaMemsetAsync(SG, 0, (size_t)p.n_sets * p.S * p.S * sizeof(long long), st));
-    SGLM_CUDA_OK(cudaMemcpyAsync(d_plane, p.plane_row.data(), p.plane_row.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    SGLM_CUDA_OK(cudaMemcpyAsync(d_tiles, p.tiles.data(), p.tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
-    SGLM_CUDA_OK(cudaMemcpyAsync(d_segs, p.segs.data(), p.segs.size() * sizeof(TcSeg), cudaMemcpyHostToDevice, st));
+    if (stage != 2) {
+        SGLM_CUDA_OK(cudaMemsetAsync(SG, 0, (size_t)p.n_sets * p.S * p.S * sizeof(long long), st));
+        SGLM_CUDA_OK(cudaMemcpyAsync(d_plane, p.plane_row.data(), p.plane_row.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        SGLM_CUDA_OK(cudaMemcpyAsync(d_tiles, p.tiles.data(), p.tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+        SGLM_CUDA_OK(cudaMemcpyAsync(d_segs, p.segs.data(), p.segs.size() * sizeof(TcSeg), cudaMemcpyHostToDevice, st));
+    }
     long long *SGout = (long long *)(ws + L.off_sgout);
     int *d_member = (int *)(ws + L.off_member);
+    if (stage == 2) {
+        // combine only: the int64 Grams of the output sets are already in the workspace (summed over the ranks)
+        SGLM_CUDA_OK(cudaMemcpyAsync(d_plane, p.plane_row.data(), p.plane_row.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        SGLM_CUDA_OK(cudaStreamSynchronize(st));
+        const long long *SGfin2 = n_out > 0 ? SGout : SG;
+        const int n_fin2 = n_out > 0 ? n_out : n_sets;
+        dim3 cgrid2((unsigned)std::min(ceil_div(n_aug, 256), 32), (unsigned)n_aug, (unsigned)n_fin2);
+        tc_combine_kernel<<<cgrid2, 256, 0, st>>>(SGfin2, p.S, colE, colS, d_plane, n_aug, G, ldg);
+        SGLM_LAUNCH_OK("tc_combine_kernel");
+        return SGLM_OK;
+    }
     if (n_out > 0)
         SGLM_CUDA_OK(cudaMemcpyAsync(d_member, member_host, (size_t)n_out * n_sets * sizeof(int), cudaMemcpyHostToDevice, st));
     SGLM_CUDA_OK(cudaStreamSynchronize(st));        // the pageable host vectors above die with this frame
@@ -901,6 +989,7 @@ static int gram_tc_run(const double *X, int64_t ldx, const double *Y, int64_t ld
         SGfin = SGout;
         n_fin = n_out;
     }
+    if (stage == 1) return SGLM_OK;                 // the caller sums the int64 set Grams over the ranks, then stage 2
     dim3 cgrid((unsigned)std::min(ceil_div(n_aug, 256), 32), (unsigned)n_aug, (unsigned)n_fin);
     tc_combine_kernel<<<cgrid, 256, 0, st>>>(SGfin, p.S, colE, colS, d_plane, n_aug, G, ldg);
     SGLM_LAUNCH_OK("tc_combine_kernel");

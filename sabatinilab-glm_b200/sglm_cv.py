@@ -174,6 +174,30 @@ class GaussianSession:
         self.G = None
         self.problems = {}
 
+    @classmethod
+    def from_statistics(cls, G, T, C, y_full, n_te, glms, rolls, score_method):
+        """A session whose statistics were computed elsewhere (sglm_dist: row-sharded over the GPUs and
+        all-reduced): G[0] = all T rows, G[1 + f] = test rows of fold f (n_te[f] of them), every train set the
+        complement of its test set.  y_full (CUDA, all T rows) only defines the y columns of the rolls."""
+        import torch
+        self = cls.__new__(cls)
+        self.Xd, self.yd, self.glms, self.rolls, self.score_method = None, y_full, glms, rolls, score_method
+        self.T, self.C, self.F = int(T), int(C), len(n_te)
+        self.cv_idx = None
+        roll_vals = [0] + sorted({r for r in rolls if r % max(self.T, 1) != 0})
+        self.roll_vals = roll_vals
+        self.ycol_of_roll = {r: k for k, r in enumerate(roll_vals)}
+        for r in rolls:
+            if r % max(self.T, 1) == 0:
+                self.ycol_of_roll[r] = 0
+        self.n_y = len(roll_vals)
+        self.Yd = None
+        self.G, self.problems = G, {}
+        self.n_te, self.n_tr = list(n_te), [self.T - n for n in n_te]
+        self.extra, self.train_set = [], {f: None for f in range(self.F)}
+        self.finite_flag = torch.isfinite(G[0]).all()
+        return self
+
     # ------------------------------------------------------------------ statistics
     def fold_sets(self):
         """Row sets of the statistics: (n_te, n_tr, extra, test_rows | None).  extra = folds whose train rows are

@@ -138,3 +138,204 @@ def _rebuild(model_name, kw, coef, intercept):
     glm.coef_ = glm.beta_ = glm.model.coef_
     glm.intercept_ = glm.beta0_ = glm.model.intercept_
     return glm
+
+
+# --------------------------------------------------------------------------- #
+# ONE grid strong-scaled over the GPUs of a box (north star: "a full CV grid ... completes on 8 x B200")
+# --------------------------------------------------------------------------- #
+last_timeline = None       # {stage: ms} of the most recent cv_grid_strong call on this rank (CUDA events)
+
+
+def deal_models(costs, world_size):
+    """Owner rank of every model: models sorted by decreasing cost and dealt in a snake (0..N-1, N-1..0, ...), so
+    every rank gets the same number of models (+-1) and a similar mix of heavy and light ones.  Returns
+    (owner[M], order[M]) with order = model indices from the most to the least expensive."""
+    costs = np.asarray(costs, dtype=np.float64)
+    order = np.argsort(-costs, kind="stable")
+    owner = np.empty(len(costs), dtype=np.int64)
+    for j, i in enumerate(order):
+        lap, pos = divmod(j, world_size)
+        owner[i] = pos if lap % 2 == 0 else world_size - 1 - pos
+    return owner, order
+
+
+def model_cost(spec):
+    """Work estimate of one fit: weakly penalised coordinate descent is heavy-tailed, direct solves are cheap."""
+    if spec.kind in ("ridge", "ols"):
+        return 0.0
+    return 1.0 / max(spec.alpha * max(spec.l1_ratio, 1e-3), 1e-300)
+
+
+def pack_results(W, b, rss_full, rss_test, rss_train, info, status, n_pad):
+    """One [n_pad, C + 10] tensor per rank: [coef (C) | intercept | rss_full | rss_test | rss_train | info (6) |
+    status]; `info` / `status` are host arrays, the rest tensors on W's device."""
+    import torch
+    n, C = W.shape
+    out = torch.zeros((n_pad, C + 11), dtype=torch.float64, device=W.device)
+    if n:
+        out[:n, :C] = W
+        out[:n, C] = b
+        out[:n, C + 1] = rss_full
+        out[:n, C + 2] = rss_test
+        out[:n, C + 3] = rss_train
+        out[:n, C + 4:C + 10] = torch.from_numpy(np.ascontiguousarray(info, dtype=np.float64)).to(W.device)
+        out[:n, C + 10] = torch.from_numpy(np.ascontiguousarray(status, dtype=np.float64)).to(W.device)
+    return out
+
+
+def unpack_results(gathered, owner_lists, C):
+    """gathered [world, n_pad, C + 11] + the model indices each rank owned (in its local order) -> per-model
+    arrays in global model order."""
+    import torch
+    M = sum(len(o) for o in owner_lists)
+    index = torch.empty(M, dtype=torch.int64)
+    pos = 0
+    n_pad = gathered.shape[1]
+    for r, mine in enumerate(owner_lists):
+        index[pos:pos + len(mine)] = r * n_pad + torch.arange(len(mine))
+        pos += len(mine)
+    flat = gathered.reshape(-1, C + 11).index_select(0, index.to(gathered.device))
+    dest = torch.from_numpy(np.concatenate([np.asarray(o, dtype=np.int64) for o in owner_lists]) if M else np.zeros(0, np.int64))
+    full = torch.empty_like(flat)
+    full.index_copy_(0, dest.to(flat.device), flat)
+    return full
+
+
+def cv_grid_strong(X0, shift_amt_list, y, cv_idx, model_name, glm_kwarg_lst, verbose=0, score_method='mse',
+                   rows=None, shift_inx=[], fill_value=np.nan, group=None, src=0):
+    """`sglm_pp.timeshift_multiple(X0, shift_inx, shift_amt_list)[rows] -> sglm_cv.cv_glm_mult_params(design, y,
+    cv_idx, ...)` for ONE session on all GPUs of the process group (NCCL).  Rank `src` passes the host (numpy) or
+    device inputs, the other ranks None; every rank gets the reference's result dict (backend/sglm_cv.py:420-426).
+
+      broadcast   base signals X0 [T, P], y and the test-row lists (a few hundred MB; never the 32 GB design)
+      gather      every rank builds ITS slice of the design rows locally (lag halo included)
+      statistics  row-sharded tcgen05 Gram of the slice; int64 plane Grams all-reduced (exact: the statistics have
+                  the bits of the one-GPU run), every rank derives the same centred problems
+      fits        models dealt to the ranks by cost; each rank runs its share of the batched plan
+      results     one packed all_gather of [coef | intercept | RSS | info]; selection on every rank
+
+    rows = (lo, hi): base rows kept after `dropna` (default: the rows without NaN padding).  Folds must be the
+    usual complement pairs with duplicate-free test rows (cv_idx_by_*); Gaussian family."""
+    import torch
+    import _engine as eng
+    import sglm_
+    import sglm_cv
+    import sglm_pp
+    global last_timeline
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ev = []
+
+    def mark(name):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        ev.append((name, e))
+
+    mark("start")
+    shifts = [int(a) for a in shift_amt_list]
+    smax, smin = max(0, max(shifts)), min(0, min(shifts))
+    # ---- source rank: inputs to the device, fold checks
+    meta = [None]
+    if rank == src:
+        X0d = eng.device_matrix(X0)
+        T, P = X0d.shape
+        lo, hi = (smax, T + smin) if rows is None else (int(rows[0]), int(rows[1]))
+        n = hi - lo
+        yd = eng.device_vector(y)
+        if yd.numel() != n:
+            raise ValueError(f"Found input variables with inconsistent numbers of samples: [{n}, {yd.numel()}]")
+        cv = sglm_cv._normalise_cv_idx(list(cv_idx), n)
+        tests = sglm_cv._unique_sorted_rows(cv, n)
+        ok = tests is not None and all(len(tr) + len(te) == n for tr, te in cv)
+        if ok:
+            _, _, _, _, comp = sglm_cv._fold_weights(cv, n)
+            ok = bool(np.all(comp))
+        meta = [dict(T=T, P=P, lo=lo, hi=hi, n_te=[int(t.numel()) for t in tests] if ok else None, ok=ok)]
+    dist.broadcast_object_list(meta, src=src, group=group)
+    m = meta[0]
+    if not m["ok"]:
+        raise NotImplementedError("cv_grid_strong needs complement train/test folds with duplicate-free test rows")
+    T, P, lo, hi, n_te = m["T"], m["P"], m["lo"], m["hi"], m["n_te"]
+    n, F = hi - lo, len(n_te)
+    if rank != src:
+        X0d = torch.empty((T, P), dtype=torch.float64, device=dev)
+        yd = torch.empty(n, dtype=torch.float64, device=dev)
+        tests = [torch.empty(k, dtype=torch.int64, device=dev) for k in n_te]
+    X0d = X0d.contiguous()
+    dist.broadcast(X0d, src=src, group=group)
+    dist.broadcast(yd, src=src, group=group)
+    packed = torch.cat(tests) if F else torch.empty(0, dtype=torch.int64, device=dev)
+    dist.broadcast(packed, src=src, group=group)
+    tests = list(torch.split(packed, n_te)) if F else []
+    mark("broadcast")
+
+    # ---- this rank's rows of the design: valid rows [g0, g1), gathered from the base rows they reach
+    g0, g1 = n * rank // world, n * (rank + 1) // world
+    a, b = max(0, lo + g0 - smax), min(T, lo + g1 - smin)
+    src_cols, sh_cols, _ = sglm_pp.build_column_map(P, shift_inx, shifts)
+    local = eng.gather(X0d[a:b], src_cols, sh_cols, fill_value)
+    off = lo + g0 - a
+    Xd = local[off: off + (g1 - g0)]
+    C = Xd.shape[1]
+    mark("gather")
+
+    # ---- parameter sets -> estimators (identical on every rank)
+    entries = []
+    for kw in glm_kwarg_lst:
+        name = kw.pop('model_name', 'Gaussian')                    # backend/sglm_cv.py:288
+        entries.append((name, kw))
+    glms, rolls = [], []
+    for name, kw in entries:
+        rolls.append(int(kw.pop('roll', 0)))                       # backend/sglm_cv.py:95
+        glms.append(sglm_.GLM(name, **kw))
+        if glms[-1].model.kind not in ("ols", "ridge", "lasso", "enet"):
+            raise NotImplementedError("cv_grid_strong: Gaussian family")
+    roll_vals = [0] + sorted({r for r in rolls if r % max(n, 1) != 0})
+    ycols = [yd if k == 0 else eng.roll_vector(yd, int(r)) for k, r in enumerate(roll_vals)]
+    Yd = torch.stack([c[g0:g1] for c in ycols], dim=1).contiguous()
+    # ---- this rank's part of every test list (sorted global lists -> local row numbers)
+    bounds = torch.tensor([g0, g1], dtype=torch.int64, device=dev)
+    local_tests = []
+    for t in tests:
+        cut = torch.searchsorted(t, bounds).cpu().numpy()
+        local_tests.append(t[int(cut[0]):int(cut[1])] - g0)
+
+    def all_reduce(t, op):
+        dist.all_reduce(t, op={"max": dist.ReduceOp.MAX, "min": dist.ReduceOp.MIN, "sum": dist.ReduceOp.SUM}[op], group=group)
+
+    G = eng.suffstats_tc_sharded(Xd, Yd, [None] + local_tests, all_reduce)
+    mark("statistics")
+    del local, Xd
+
+    ses = sglm_cv.GaussianSession.from_statistics(G, n, C, yd, n_te, glms, rolls, score_method)
+    models = ses.model_specs()
+    M = len(models)
+    owner, _ = deal_models([model_cost(s) for s in models], world)
+    owner_lists = [np.flatnonzero(owner == r) for r in range(world)]
+    mine = owner_lists[rank]
+    mark("problems")
+    W, info, status = eng.solve_models([models[i] for i in mine], C)
+    mark("fits")
+    b_d, rss_full, rss_test, rss_train = ses.score(W, mine)
+    n_pad = max(len(o) for o in owner_lists) if M else 0
+    mine_pack = pack_results(W[:, :C], b_d, rss_full, rss_test, rss_train, info, status, n_pad)
+    gathered = torch.empty((world, n_pad, C + 11), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(gathered.reshape(world * n_pad, C + 11), mine_pack, group=group)
+    mark("scores+all_gather")
+    full = unpack_results(gathered, owner_lists, C)
+
+    n_sets = len(glms)
+    W3 = full[:, :C].reshape(n_sets, F + 1, C)
+    coef_folds = W3[:, :F, :].permute(0, 2, 1).contiguous().cpu().numpy()
+    coef_full = W3[:, F, :].contiguous().cpu().numpy()
+    tail = full[:, C:].cpu().numpy()
+    res = ses.assemble(coef_folds, coef_full, tail[:, 0].copy(), tail[:, 2].copy(), tail[:, 3].copy(),
+                       tail[:, 4:10].copy(), tail[:, 10].astype(np.int64))
+    for (name, kw), r in zip(entries, res):
+        r['glm_kwargs'] = kw
+    mark("download+assemble")
+    torch.cuda.synchronize()
+    last_timeline = {name: float(ev[k - 1][1].elapsed_time(e)) for k, (name, e) in enumerate(ev) if k > 0}
+    last_timeline["models_on_this_rank"] = int(len(mine))
+    return sglm_cv._select_best([sglm_cv._order_result(r) for r in res], score_method)
