@@ -342,6 +342,40 @@ int sglm_poisson_irls_prepare_f64(const double *X, int64_t ldx, const double *y,
                                   double *weight, double *z, double *sums, void *workspace,
                                   void *stream);
 
+/* Batched triangular solves with cached factors: out[s] = (L_s L_s')^-1 rhs[s] for every system s with
+ * flags[s] == 1 (flags may be NULL); L_of[s] = factor left by sglm_ridge_solve_f64 (work + k (C+1) ldq doubles). */
+int sglm_chol_solve_batched_f64(const double *const *L_of, int64_t ldq, int32_t C, const double *rhs, double *out,
+                                int64_t ld, const int32_t *flags, int32_t n_systems, void *stream);
+
+/* ------------------------------------------------------------------------- *
+ * (a9, batched) Poisson grid: all (fold, alpha) fits of a sweep advance together.  Replaces the per-(fold, alpha)
+ * TweedieRegressor(power=1).fit calls of backend/sglm.py:112-115, :241 (sklearn _glm/glm.py:185-339).  One
+ * iteration of the whole batch of B models (columns of Wt [C][ldb], ldb % 64 == 0):
+ *   sglm_pb_eta_f64       Eta [T][ldb] = X Wt                        (fp64 GEMM: X read once for all models)
+ *   sglm_pb_epilogue_f64  mode 0: Eta <- R = rw (exp(Eta + b) - y) in place, sums [B][4] =
+ *                                 {sum rw (mu - y eta), sum rw mu, sum rw, sum rw (mu - y)};
+ *                         mode 1: sums [B][2][8] = the sglm_score_f64 sums for the row weights rw_a / rw_b
+ *                         (Y [T][ldy] response columns, ycol[m]; RW [n_w][ldrw] row-weight vectors, rw id -1 = all
+ *                         rows, rw_b id -2 = no rows; models with status != 0 are skipped in mode 0)
+ *   sglm_pb_xt_r_f64      Gw [C][ldb] = X' R                         (fp64 GEMM, deterministic split over T)
+ *   sglm_pb_step_f64      per model: objective check / step halving, rhs = H~ w - g, batched triangular solves
+ *                         with the cached factors L_of[m] of (H~ + alpha n I), intercept, convergence test.
+ *                         state_host: the solver state (device pointers and sizes) as sglm_pb_state_words()
+ *                         64-bit words — see PbState in csrc/poisson_batch.cu; built by _engine.py.
+ * H~ = X' diag(rw mu_ref) X of one reference model per fold comes from sglm_gram_tc_scaled_f64 (tcgen05). */
+size_t sglm_pb_gemm_tn_workspace_bytes(int64_t T, int32_t C, int64_t ldb);
+int sglm_pb_eta_f64(const double *X, int64_t ldx, int64_t T, int32_t C, const double *Wt, int64_t ldb, double *Eta,
+                    void *stream);
+int sglm_pb_xt_r_f64(const double *X, int64_t ldx, int64_t T, int32_t C, const double *R, int64_t ldb, double *Gw,
+                     void *workspace, size_t workspace_bytes, void *stream);
+size_t sglm_pb_epilogue_workspace_bytes(int64_t T, int32_t n_models);
+int sglm_pb_epilogue_f64(double *Eta, int64_t ldb, int32_t n_models, int64_t T, const double *Y, int64_t ldy,
+                         const int32_t *ycol, const double *RW, int64_t ldrw, const int32_t *rw_a,
+                         const int32_t *rw_b, const double *b, const int32_t *status, int32_t mode, double *sums,
+                         void *workspace, size_t workspace_bytes, void *stream);
+int sglm_pb_state_words(void);
+int sglm_pb_step_f64(const uint64_t *state_host, const double *const *L_of, void *stream);
+
 /* ------------------------------------------------------------------------- *
  * Measurement probe (bench.py; no reference counterpart): reads `n_doubles` doubles
  * `repeats` times with the access pattern of the coordinate-descent panel (16-byte

@@ -977,3 +977,209 @@ def poisson_irls(Xd, yd, alpha, fit_intercept=True, rw=None, max_iter=100, tol=1
         refresh = step > 0.2 * last_step          # chord steps must keep contracting by 5x, else a new Hessian
         last_step = step
     return w[:C].cpu().numpy(), float(b.item()) if fit_intercept else 0.0, n_iter
+
+
+# --------------------------------------------------------------------------- #
+# (a9, batched) Poisson grid: all (fold, alpha) fits advance together (csrc/poisson_batch.cu)
+# --------------------------------------------------------------------------- #
+PB_MAX_BATCH = 256       # models per batch (Eta is T x round_up(B, 64) doubles)
+last_poisson_batch = None    # diagnostics of the most recent batch: iterations, Hessian refreshes
+
+
+class PoissonModel:
+    """One Poisson fit of a batch: penalty, row-weight vector (index into RW, -1 = all rows), response column."""
+    __slots__ = ("alpha", "fit_intercept", "rw", "ycol", "max_iter", "tol", "n_tot")
+
+    def __init__(self, alpha, fit_intercept=True, rw=-1, ycol=0, max_iter=100, tol=1e-4, n_tot=None):
+        self.alpha, self.fit_intercept, self.rw, self.ycol = float(alpha), bool(fit_intercept), int(rw), int(ycol)
+        self.max_iter, self.tol, self.n_tot = int(max_iter), float(tol), n_tot
+
+
+def _pb_hessian(Xd, y_col, rw_vec, w_ref, b_ref, fit_intercept, n_tot, use_tc):
+    """H~ = X' diag(rw mu_ref) X (centred on the weighted column means when an intercept is fitted) of one reference
+    model: the fused row pass gives the weights, the tcgen05 digit-plane Gram (large problems) or the fp64 DMMA Gram
+    the matrix.  Returns (Problem-like hess with Qc / xbar, h11 = sum of the weights as a device scalar)."""
+    torch = nat.require_cuda()
+    T, C = Xd.shape
+    sums = _empty((8,))
+    ws = torch.empty(nat.lib().sglm_score_workspace_bytes() // 8, dtype=torch.float64, device="cuda")
+    weight = _empty((1, T))
+    z = _empty((T, 1))
+    call("sglm_poisson_irls_prepare_f64", ptr(Xd), row_stride(Xd), ptr(y_col), ptr(rw_vec), T, C, ptr(w_ref), ptr(b_ref),
+         ptr(weight), ptr(z), ptr(sums), ptr(ws), stream_ptr())
+    if use_tc:
+        G = suffstats_tc_scaled(Xd, z, weight[0].sqrt(), POISSON_TC_PLANES)
+    else:
+        G = suffstats(Xd, z, weight, [n_tot])
+    hess = center(G[0], None, C, 1, 0, fit_intercept)
+    return hess, sums[1:2].clone()
+
+
+def poisson_grid_batched(Xd, Yd, models, RW=None):
+    """Fit every PoissonModel of `models` on (Xd, Yd[:, ycol]) with row weights RW[rw] — argmin mean(mu - y eta) +
+    alpha/2 |w|^2 over the weighted rows — as ONE batched iteration (see csrc/poisson_batch.cu).  Returns
+    (W [B, C] CUDA, b [B] CUDA, n_iter [B] host, status [B] host: 1 converged, 2 max_iter)."""
+    torch = nat.require_cuda()
+    global last_poisson_batch
+    T, C = Xd.shape
+    out_W, out_b, out_it, out_st = [], [], [], []
+    diag = []
+    for c0 in range(0, len(models), PB_MAX_BATCH):
+        Wb, bb, it, st, dg = _poisson_batch(Xd, Yd, models[c0:c0 + PB_MAX_BATCH], RW)
+        out_W.append(Wb); out_b.append(bb); out_it.append(it); out_st.append(st); diag.append(dg)
+    last_poisson_batch = diag
+    return torch.cat(out_W), torch.cat(out_b), np.concatenate(out_it), np.concatenate(out_st)
+
+
+def _poisson_batch(Xd, Yd, models, RW):
+    torch = nat.require_cuda()
+    T, C = Xd.shape
+    B = len(models)
+    ldb = _round_up(B, 64)
+    ldw = _round_up(C, 2)
+    ldy = Yd.stride(0)
+    n_w = 0 if RW is None else RW.shape[0]
+    # ---- per-model constants: rows in the fit, weighted mean of y (start point b = log ybar, sklearn glm.py:264-270)
+    ycontig = {}
+    combos = sorted({(m.rw, m.ycol) for m in models})
+    stats = torch.stack([torch.stack([(RW[rw].sum() if rw >= 0 else torch.tensor(float(T), device="cuda", dtype=torch.float64)),
+                                      ((RW[rw] * Yd[:, yc]).sum() if rw >= 0 else Yd[:, yc].sum()),
+                                      Yd[:, yc].min()]) for rw, yc in combos]).cpu().numpy()
+    info = {k: v for k, v in zip(combos, stats)}
+    if any(v[2] < 0 for v in info.values()) or any(not (v[1] > 0) for v in info.values()):
+        raise ValueError("Some value(s) of y are out of the valid range of the loss 'HalfPoissonLoss'.")
+    n_tot = np.array([info[(m.rw, m.ycol)][0] for m in models])
+    b0 = np.array([np.log(info[(m.rw, m.ycol)][1] / info[(m.rw, m.ycol)][0]) if m.fit_intercept else 0.0 for m in models])
+    for yc in {m.ycol for m in models}:
+        ycontig[yc] = Yd[:, yc].contiguous()
+    # ---- state on the device
+    f64, i32 = np.float64, np.int32
+    W, Wprev, Wnew, rhs = (_zeros((B, ldw)) for _ in range(4))
+    b = _dev(b0, f64)
+    bprev, fprev, fcur, last_step, step_out, ratio_out = (_zeros((B,)) for _ in range(6))
+    zi = lambda: torch.zeros(B, dtype=torch.int32, device="cuda")
+    halv, n_iter, status, flag, has_prev = zi(), zi(), zi(), zi(), zi()
+    alpha = _dev([m.alpha for m in models], f64)
+    n_tot_d = _dev(n_tot, f64)
+    tol = _dev([m.tol for m in models], f64)
+    fit_icpt = _dev([int(m.fit_intercept) for m in models], i32)
+    max_iter = _dev([m.max_iter for m in models], i32)
+    groups = {}
+    for i, m in enumerate(models):
+        groups.setdefault((m.rw, m.fit_intercept), []).append(i)
+    gkeys = list(groups)
+    hess_id = _dev([gkeys.index((m.rw, m.fit_intercept)) for m in models], i32)
+    ycol = _dev([m.ycol for m in models], i32)
+    rw_a = _dev([m.rw for m in models], i32)
+    sums = _zeros((B, 4))
+    Gw = _zeros((C, ldb))
+    Wt = _zeros((C, ldb))
+    Eta = _empty((max(T, 1), ldb))
+    xt_bytes = nat.lib().sglm_pb_gemm_tn_workspace_bytes(T, C, ldb)
+    xt_ws = torch.empty(xt_bytes // 8 + 1, dtype=torch.float64, device="cuda")
+    ep_bytes = nat.lib().sglm_pb_epilogue_workspace_bytes(T, B)
+    ep_ws = torch.empty(ep_bytes // 8 + 1, dtype=torch.float64, device="cuda")
+    ldq = _round_up(C, 8)
+    # ---- Hessians (one per fold / intercept setting) and the factors of (H~ + alpha n I) of every model
+    use_tc = _poisson_tc(T, C)
+    n_h = len(gkeys)
+    HQ = torch.zeros(n_h, dtype=torch.int64, device="cuda")
+    Hxbar = torch.zeros(n_h, dtype=torch.int64, device="cuda")
+    Hh11 = _zeros((n_h,))
+    L_of = torch.zeros(B, dtype=torch.int64, device="cuda")
+    keep = {}
+    wb_of = {}
+
+    def refresh(g, ref):
+        """New H~ of group g from the current iterate of model `ref`, new factors for the group's models."""
+        rw, fi = gkeys[g]
+        idxs = groups[gkeys[g]]
+        rw_vec = RW[rw] if rw >= 0 else None
+        hess, h11 = _pb_hessian(Xd, ycontig[models[ref].ycol], rw_vec, W[ref], b[ref:ref + 1], fi, float(n_tot[ref]), use_tc)
+        an = _dev([models[i].alpha * n_tot[i] for i in idxs], f64)
+        wb = nat.lib().sglm_ridge_workspace_bytes(C, hess.ldq, len(idxs))
+        work = torch.empty(wb // 8, dtype=torch.float64, device="cuda")
+        Wtmp = _empty((len(idxs), ldw))
+        st = torch.empty(len(idxs), dtype=torch.int32, device="cuda")
+        call("sglm_ridge_solve_f64", ptr(hess.Qc), hess.ldq, ptr(hess.qc), C, ptr(an), len(idxs), ptr(Wtmp), ldw, ptr(st),
+             ptr(work), wb, stream_ptr())
+        keep[g] = (hess, work, h11)           # the previous Hessian / factors of the group are released here
+        HQ[g] = hess.Qc.data_ptr()
+        Hxbar[g] = hess.xbar.data_ptr()
+        Hh11[g:g + 1] = h11
+        stride = (C + 1) * hess.ldq * 8
+        L_of[_dev(idxs, np.int64)] = _dev([work.data_ptr() + k * stride for k in range(len(idxs))], np.int64)
+        last_step[_dev(idxs, np.int64)] = 0.0     # the contraction estimate restarts with the new Hessian
+
+    for g in range(n_h):
+        refresh(g, groups[gkeys[g]][0])
+    n_words = nat.lib().sglm_pb_state_words()
+    fields = [W, Wprev, Wnew, rhs, b, bprev, fprev, fcur, last_step, step_out, ratio_out, halv, n_iter, status, flag,
+              has_prev, alpha, n_tot_d, tol, fit_icpt, max_iter, hess_id, HQ, Hxbar, Hh11, sums, Gw]
+    words = [t.data_ptr() for t in fields] + [ldw, ldq, ldb, C | (B << 32)]
+    if len(words) != n_words:
+        raise nat.SglmNativeError(f"poisson batch: state layout mismatch ({len(words)} words, library expects {n_words})")
+    state = np.array(words, dtype=np.uint64)
+    state_p = state.ctypes.data_as(ctypes.c_void_p)
+    RWp, ldrw = (ptr(RW), RW.stride(0)) if RW is not None else (None, 0)
+    refreshed_at = {g: 0 for g in range(n_h)}
+    n_refresh = {g: 1 for g in range(n_h)}
+    it = 0
+    max_rounds = int(max(m.max_iter for m in models)) + 40
+    while it < max_rounds:
+        Wt[:, :B] = W[:, :C].t()
+        call("sglm_pb_eta_f64", ptr(Xd), row_stride(Xd), T, C, ptr(Wt), ldb, ptr(Eta), stream_ptr())
+        call("sglm_pb_epilogue_f64", ptr(Eta), ldb, B, T, ptr(Yd), ldy, ptr(ycol), RWp, ldrw, ptr(rw_a), None, ptr(b),
+             ptr(status), 0, ptr(sums), ptr(ep_ws), ep_ws.numel() * 8, stream_ptr())
+        call("sglm_pb_xt_r_f64", ptr(Xd), row_stride(Xd), T, C, ptr(Eta), ldb, ptr(Gw), ptr(xt_ws), xt_ws.numel() * 8,
+             stream_ptr())
+        call("sglm_pb_step_f64", state_p, ptr(L_of), stream_ptr())
+        it += 1
+        host = torch.stack([status.to(torch.float64), step_out, ratio_out]).cpu().numpy()     # the one read-back per iteration
+        st_h, step_h, ratio_h = host[0], host[1], host[2]
+        if np.all(st_h != 0):
+            break
+        # refresh policy: after the first step (the start Hessian belongs to mu = const), then whenever the steps of a
+        # fold stop contracting by at least 3x per iteration; reference = the active model with the largest step
+        for g in range(n_h):
+            idxs = np.array(groups[gkeys[g]])
+            act = idxs[st_h[idxs] == 0]
+            if len(act) == 0 or n_refresh[g] >= 8:
+                continue
+            taken = act[step_h[act] > 0]
+            slow = len(taken) and np.max(ratio_h[taken]) > 0.35 and np.max(step_h[taken]) > 1e-7
+            if (n_refresh[g] == 1 and it >= 1) or (slow and it - refreshed_at[g] >= 2):
+                ref = int(act[np.argmax(np.abs(step_h[act]))])
+                refresh(g, ref)
+                refreshed_at[g], n_refresh[g] = it, n_refresh[g] + 1
+    n_it = n_iter.cpu().numpy().astype(np.int64)
+    st_f = status.cpu().numpy().astype(np.int64)
+    st_f[st_f == 0] = 2
+    return W[:, :C].contiguous(), b.clone(), n_it, st_f, dict(rounds=it, refreshes=dict(n_refresh), models=B,
+                                                              hessian_groups=n_h, tensor_core_hessian=bool(use_tc))
+
+
+def poisson_scores_batched(Xd, Yd, W, b, ycol, rw_a, rw_b, RW):
+    """Score sums of B fitted Poisson models in one pass over X: sums [B, 2, 8] (host) for the row weights rw_a /
+    rw_b of each model (-1: all rows; rw_b = -2: none) — {n, sum r^2, sum y, sum y^2, sum y eta, sum mu,
+    sum y log y, sum r}, the inputs of D^2 / -MSE / pooled R^2 (sglm_score_f64 semantics)."""
+    torch = nat.require_cuda()
+    T, C = Xd.shape
+    B = W.shape[0]
+    out = np.zeros((B, 2, 8))
+    for c0 in range(0, B, PB_MAX_BATCH):
+        n = min(PB_MAX_BATCH, B - c0)
+        ldb = _round_up(n, 64)
+        Wt = _zeros((C, ldb))
+        Wt[:, :n] = W[c0:c0 + n, :C].t()
+        Eta = _empty((max(T, 1), ldb))
+        call("sglm_pb_eta_f64", ptr(Xd), row_stride(Xd), T, C, ptr(Wt), ldb, ptr(Eta), stream_ptr())
+        sums = _zeros((n, 16))
+        ep_bytes = nat.lib().sglm_pb_epilogue_workspace_bytes(T, n)
+        ep_ws = torch.empty(ep_bytes // 8 + 1, dtype=torch.float64, device="cuda")
+        call("sglm_pb_epilogue_f64", ptr(Eta), ldb, n, T, ptr(Yd), Yd.stride(0), ptr(_dev(ycol[c0:c0 + n], np.int32)),
+             ptr(RW) if RW is not None else None, RW.stride(0) if RW is not None else 0,
+             ptr(_dev(rw_a[c0:c0 + n], np.int32)), ptr(_dev(rw_b[c0:c0 + n], np.int32)), ptr(b[c0:c0 + n].contiguous()),
+             None, 1, ptr(sums), ptr(ep_ws), ep_ws.numel() * 8, stream_ptr())
+        out[c0:c0 + n] = sums.cpu().numpy().reshape(n, 2, 8)
+    return out

@@ -821,10 +821,29 @@ ridge_cholesky_ll_kernel(const double *__restrict__ Qc, long long ldq, const dou
 // every thread corrects its rows with 32 contiguous factor entries) and blocked back substitution
 // (column access of L is contiguous across threads).  Used by the Poisson Newton iteration to reuse a
 // Hessian factor over several steps (chord iterations): 2 * C^2/2 * 8 bytes of factor traffic per solve.
+__device__ __forceinline__ void chol_solve_body(const double *__restrict__ L, long long ldq, int C,
+                                                const double *__restrict__ rhs, double *__restrict__ out, double *sh);
+
 __global__ void __launch_bounds__(RC_THREADS)
 chol_solve_kernel(const double *__restrict__ L, long long ldq, int C, const double *__restrict__ rhs,
                   double *__restrict__ out) {
     extern __shared__ __align__(16) double sh[];
+    chol_solve_body(L, ldq, C, rhs, out, sh);
+}
+
+// One CTA per system: factor pointers L_of[s], right-hand sides / solutions as rows of [n][ld] matrices; systems whose
+// flag is not 1 are skipped (the batched Poisson Newton iteration solves only the models that take a step).
+__global__ void __launch_bounds__(RC_THREADS)
+chol_solve_batched_kernel(const double *const *__restrict__ L_of, long long ldq, int C, const double *__restrict__ rhs,
+                          double *__restrict__ out, long long ld, const int *__restrict__ flags) {
+    extern __shared__ __align__(16) double sh[];
+    const int s = blockIdx.x;
+    if (flags && flags[s] != 1) return;
+    chol_solve_body(L_of[s], ldq, C, rhs + (long long)s * ld, out + (long long)s * ld, sh);
+}
+
+__device__ __forceinline__ void chol_solve_body(const double *__restrict__ L, long long ldq, int C,
+                                                const double *__restrict__ rhs, double *__restrict__ out, double *sh) {
     double *D = sh;                          // [32][33] diagonal block
     double *xv = D + RC_NB * 33;             // [C] running right-hand side / solution
     const int tid = threadIdx.x;
@@ -1061,6 +1080,20 @@ extern "C" int sglm_ridge_solve_f64(const double *Qc, int64_t ldq, const double 
     ridge_cholesky_ll_kernel<<<n_alpha, RC_THREADS, smem, (cudaStream_t)stream>>>(Qc, ldq, qc, C, alpha, W, ldw, status,
                                                                                  (double *)work);
     SGLM_LAUNCH_OK("ridge_cholesky_ll_kernel");
+    return SGLM_OK;
+}
+
+extern "C" int sglm_chol_solve_batched_f64(const double *const *L_of, int64_t ldq, int32_t C, const double *rhs,
+                                           double *out, int64_t ld, const int32_t *flags, int32_t n_systems,
+                                           void *stream) {
+    SGLM_CHECK_ARG(C > 0 && ldq >= C && ld >= C && n_systems >= 0, SGLM_E_SHAPE, "chol_solve_batched: bad shape");
+    if (n_systems == 0) return SGLM_OK;
+    SGLM_CHECK_ARG(L_of && rhs && out, SGLM_E_INVALID_ARG, "chol_solve_batched: null pointer");
+    const size_t smem = (size_t)(RC_NB * 33 + C) * sizeof(double);
+    SGLM_CHECK_ARG(smem <= 227 * 1024, SGLM_E_UNSUPPORTED, "chol_solve_batched: C=%d too large for shared memory", C);
+    SGLM_CUDA_OK(cudaFuncSetAttribute(chol_solve_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    chol_solve_batched_kernel<<<n_systems, RC_THREADS, smem, (cudaStream_t)stream>>>(L_of, ldq, C, rhs, out, ld, flags);
+    SGLM_LAUNCH_OK("chol_solve_batched_kernel");
     return SGLM_OK;
 }
 

@@ -471,35 +471,47 @@ def _set_fitted(glm, coef, intercept, info, status):
 
 
 def _poisson_grid(Xd, yd, cv_idx, glms, rolls, score_method):
-    """Poisson family: one IRLS solve per (param set, fold) on fold row-weights."""
+    """Poisson family (backend/sglm.py:112-115): every (parameter set, fold) fit and every refit of the grid as ONE
+    batched Newton-type iteration (`_engine.poisson_grid_batched`: X is read once per iteration for all models,
+    one tcgen05 weighted Gram per fold as the shared approximate Hessian, exact gradients), then one batched
+    scoring pass for the train / test sums of every fold model."""
     import torch
     T, C = Xd.shape
     F = len(cv_idx)
     _, te_w, _, n_te, _ = _fold_weights(cv_idx, T)
     tr_w = [eng.index_counts(train, T) for (train, _) in cv_idx]
-    results = []
-    # Every IRLS run is driven to the optimum (Newton step below 1e-8), so the starting point only changes the
-    # number of iterations: the refit starts from the previous parameter set's refit, the folds from the refit
-    # of their own parameter set (a few Newton steps instead of a cold start from log(mean y)).
-    prev_full = None
+    RW = torch.stack(tr_w + te_w).contiguous() if F else None             # rows 0..F-1 train, F..2F-1 test weights
+    if not bool(torch.isfinite(Xd).all().item()):
+        raise ValueError("Input X contains NaN or infinity.")
+    roll_vals = [0] + sorted({r for r in rolls if r % max(T, 1) != 0})
+    ycol_of_roll = {r: k for k, r in enumerate(roll_vals)}
+    for r in rolls:
+        if r % max(T, 1) == 0:
+            ycol_of_roll[r] = 0
+    Yd = torch.stack([yd if k == 0 else eng.roll_vector(yd, int(r)) for k, r in enumerate(roll_vals)], dim=1).contiguous()
+    models, ycol, rw_a, rw_b = [], [], [], []
     for glm, r in zip(glms, rolls):
         est = glm.model
         est._check_family()
-        y_r = torch.roll(yd, int(r)) if r else yd
-        cv_coefs = np.zeros((C, F))
-        cv_intercepts = np.zeros(F)
+        for f in range(F):
+            models.append(eng.PoissonModel(est.alpha, est.fit_intercept, rw=f, ycol=ycol_of_roll[r],
+                                           max_iter=est.max_iter, tol=est.tol))
+            ycol.append(ycol_of_roll[r]); rw_a.append(f); rw_b.append(F + f)
+        models.append(eng.PoissonModel(est.alpha, est.fit_intercept, rw=-1, ycol=0, max_iter=est.max_iter, tol=est.tol))
+        ycol.append(0); rw_a.append(-1); rw_b.append(-2)          # the refit uses the UN-rolled y (backend/sglm_cv.py:181)
+    Wd, bd, n_it, status = eng.poisson_grid_batched(Xd, Yd, models, RW)
+    sums = eng.poisson_scores_batched(Xd, Yd, Wd, bd, ycol, rw_a, rw_b, RW)
+    W_h, b_h = Wd.cpu().numpy(), bd.cpu().numpy()
+    results = []
+    for k, glm in enumerate(glms):
+        est = glm.model
+        base = k * (F + 1)
+        cv_coefs = np.ascontiguousarray(W_h[base:base + F].T) if F else np.zeros((C, 0))
+        cv_intercepts = b_h[base:base + F].copy() if est.fit_intercept else np.zeros(F)
         s_tr, s_te = np.zeros(F), np.zeros(F)
         rss_pool = tss_pool = n_pool = 0.0
-        init = prev_full if (prev_full is not None and prev_full[2] == bool(est.fit_intercept)) else (None, None, None)
-        w_full, b_full, n_it_full = eng.poisson_irls(Xd, yd, est.alpha, est.fit_intercept, None, est.max_iter, est.tol,
-                                                     coef_init=init[0], intercept_init=init[1])
-        prev_full = (w_full, b_full, bool(est.fit_intercept))
         for f in range(F):
-            w, b, _ = eng.poisson_irls(Xd, y_r, est.alpha, est.fit_intercept, tr_w[f], est.max_iter, est.tol,
-                                       coef_init=w_full if not r else None, intercept_init=b_full if not r else None)
-            cv_coefs[:, f], cv_intercepts[f] = w, b
-            st, _ = eng.score_sums(Xd, y_r, w, b, 1, rw=tr_w[f])
-            se, _ = eng.score_sums(Xd, y_r, w, b, 1, rw=te_w[f])
+            st, se = sums[base + f, 0], sums[base + f, 1]
             if score_method == 'r2':
                 s_tr[f], s_te[f] = eng.poisson_d2_from_sums(st), eng.poisson_d2_from_sums(se)
             else:
@@ -507,18 +519,20 @@ def _poisson_grid(Xd, yd, cv_idx, glms, rolls, score_method):
             rss_pool += se[1]
             tss_pool += se[3] - se[2] * se[2] / se[0]
             n_pool += se[0]
-        w, b, n_it = w_full, b_full, n_it_full
-        est.coef_, est.intercept_, est.n_iter_ = w, b, n_it
+        w, b = W_h[base + F].copy(), float(b_h[base + F]) if est.fit_intercept else 0.0
+        est.coef_, est.intercept_, est.n_iter_ = w, b, int(n_it[base + F])
+        est.n_features_in_ = C
         glm.coef_ = glm.beta_ = w
         glm.intercept_ = glm.beta0_ = b
         results.append({
             'cv_coefs': cv_coefs, 'cv_intercepts': cv_intercepts,
             'cv_scores_train': s_tr, 'cv_scores_test': s_te,
-            'cv_mean_score_train': np.mean(s_tr), 'cv_mean_score': np.mean(s_te),
-            'cv_std_score': np.std(s_te),
+            'cv_mean_score_train': np.mean(s_tr) if F else np.nan, 'cv_mean_score': np.mean(s_te) if F else np.nan,
+            'cv_std_score': np.std(s_te) if F else np.nan,
             'cv_R2_score': 0 if tss_pool == 0 else 1 - rss_pool / tss_pool,
             'cv_mse_score': rss_pool / n_pool if n_pool else np.nan,
             'model': glm,
+            '_fit_info': {'n_iter': n_it[base:base + F + 1], 'status': status[base:base + F + 1]},
         })
     return results
 

@@ -345,3 +345,74 @@ def test_ols_lag_design_with_duplicated_and_near_duplicated_columns():
     assert np.isfinite(g.coef_).all() and np.abs(g.coef_).max() < 1e3 * max(1.0, np.abs(ref.coef_).max())
     # a well-conditioned design takes the plain Cholesky path and still matches
     _ols_vs_sklearn(Xd, y, coef_tol=1e-7)
+
+
+def test_poisson_batched_grid_vs_oracle_and_sklearn():
+    """BASELINE configs[3] shape (20 predictors x 40 shifts = 800 columns) at reduced T: the batched Poisson grid
+    (all (fold, alpha) fits advance together, one shared Hessian per fold, exact gradients) against the oracle's
+    per-fit Newton solves (optimum, 1e-6) and against TweedieRegressor driven to its optimum; with the exact fp64
+    Hessian and with the tcgen05 digit-plane Hessian."""
+    import sglm
+    from sklearn.linear_model import TweedieRegressor
+    T, P = 12_000, 20
+    shifts = [0] + [s for s in range(-20, 20) if s != 0]
+    X0 = synth_data.synth_base(T, P, 404)
+    Xd = orc.timeshift_multiple(X0, shift_amt_list=shifts)
+    Xd = Xd[~np.isnan(Xd).any(axis=1)]
+    assert Xd.shape[1] == 800
+    y = synth_data.synth_response(Xd, synth_data.synth_kernels(P, shifts, 404), 404, poisson=True)
+    cv_idx = synth_data.synth_folds(Xd.shape[0], 3, 404, group=500)
+    grid = [dict(alpha=a) for a in (1e-3, 1e-2, 0.1, 1.0)] + [dict(alpha=0.05, fit_intercept=False), dict(alpha=0.02, roll=5)]
+    want = orc.cv_glm_mult_params(Xd, y, cv_idx, "Poisson", [dict(k) for k in grid], score_method="r2")
+    old = eng.POISSON_TC
+    try:
+        for use_tc in (False, True):
+            eng.POISSON_TC = use_tc
+            got = sglm_cv.cv_glm_mult_params(Xd, y, cv_idx, "Poisson", [dict(k) for k in grid], score_method="r2")
+            diag = eng.last_poisson_batch[0]
+            assert diag["models"] == len(grid) * 4 and diag["tensor_core_hessian"] == use_tc
+            assert diag["rounds"] <= 40, diag
+            assert got["best_params"] == want["best_params"]
+            assert abs(got["best_score"] - want["best_score"]) < 1e-6
+            for a, b in zip(got["full_cv_results"], want["full_cv_results"]):
+                assert np.all(a["_fit_info"]["status"] == 1), (a["glm_kwargs"], a["_fit_info"])
+                for k in range(3):
+                    assert coef_rel_err(a["cv_coefs"][:, k], b["cv_coefs"][:, k]) < 1e-6, (use_tc, a["glm_kwargs"], k)
+                assert np.allclose(a["cv_intercepts"], b["cv_intercepts"], atol=1e-7)
+                assert np.allclose(a["cv_scores_test"], b["cv_scores_test"], atol=1e-6)
+                assert np.allclose(a["cv_scores_train"], b["cv_scores_train"], atol=1e-6)
+                assert abs(a["cv_R2_score"] - b["cv_R2_score"]) < 1e-6 and abs(a["cv_mse_score"] - b["cv_mse_score"]) < 1e-6
+                assert coef_rel_err(a["model"].coef_, b["model"].coef_) < 1e-6
+    finally:
+        eng.POISSON_TC = old
+    ref = TweedieRegressor(power=1, alpha=0.1, solver="newton-cholesky", tol=1e-12, max_iter=1000).fit(Xd, y)
+    r = got["full_cv_results"][2]
+    assert coef_rel_err(r["model"].coef_, ref.coef_) < 1e-6 and abs(r["model"].intercept_ - ref.intercept_) < 1e-7
+
+
+def test_poisson_d2_gap_to_the_reference_default_solver():
+    """What the reference's own call returns — TweedieRegressor(power=1) with its default L-BFGS solver stopped at
+    gtol = 1e-4 (fixture `coefs_default`, generated from scikit-learn in the build container) — is up to 15 % away
+    from the optimum in coefficients at small alpha; in the quantity the CV grid selects on, D^2, the GPU result
+    (the optimum) is within 2e-4 of it, and its penalised objective is never worse."""
+    from conftest import load_golden
+    import sglm
+    blob, meta = load_golden("poisson_ref")
+    Xd = orc.timeshift_multiple(blob["X0"], shift_amt_list=[int(s) for s in blob["shifts"]])[blob["keep"]]
+    y = blob["y"]
+    n = len(y)
+
+    def objective(w, b, alpha):
+        eta = Xd @ w + b
+        return float(np.mean(np.exp(eta) - y * eta) + 0.5 * alpha * (w @ w))
+    worst = 0.0
+    for i, kw in enumerate(meta["grid"]):
+        g = sglm.GLM("Poisson", **dict(kw))
+        g.fit(Xd, y)
+        mu_d = np.exp(Xd @ blob["coefs_default"][i] + blob["intercepts_default"][i])
+        d2_default = orc.poisson_d2(y, mu_d)
+        d2_gpu = g.r2_score(Xd, y)
+        worst = max(worst, abs(d2_gpu - d2_default))
+        assert abs(d2_gpu - d2_default) < 2e-4, (kw, d2_gpu, d2_default)
+        assert objective(g.coef_, g.intercept_, kw["alpha"]) <= objective(blob["coefs_default"][i], blob["intercepts_default"][i], kw["alpha"]) + 1e-12
+    assert worst > 1e-6          # the gap is real: the default solver does stop early
