@@ -342,6 +342,26 @@ int sglm_poisson_irls_prepare_f64(const double *X, int64_t ldx, const double *y,
                                   double *weight, double *z, double *sums, void *workspace,
                                   void *stream);
 
+/* ------------------------------------------------------------------------- *
+ * Steps either side of the lag builder, for data already on the device:
+ *   col_moments + zscore_apply : sglm_pp.zscore (backend/sglm_pp.py:105-118): (X - mean) / std per column; ddof 0 =
+ *                   numpy std (ndarray input), 1 = pandas std (DataFrame input); skipna as pandas does.
+ *   diff1         : one first difference of the listed columns (sglm_pp.diff, :120-190; the n-th difference is n
+ *                   calls, the way np.diff computes it — bit-exact).
+ *   rolling_minmax: sglm_pp.detrend_data (:522-545): pandas rolling(window, center=True).apply(lambda_min_max) —
+ *                   the window's element (W+1)//2 - 1 scaled by the window's 5 % / 95 % quantiles (linear
+ *                   interpolation); NaN where the window leaves its group segment or holds a NaN.
+ * ------------------------------------------------------------------------- */
+size_t sglm_col_moments_workspace_bytes(int64_t T, int32_t C);
+int sglm_col_moments_f64(const double *X, int64_t ldx, int64_t T, int32_t C, int32_t ddof, int32_t skipna,
+                         double *mean, double *sd, void *workspace, size_t workspace_bytes, void *stream);
+int sglm_zscore_apply_f64(const double *X, int64_t ldx, int64_t T, int32_t C, const double *mean, const double *sd,
+                          double *out, int64_t ldo, void *stream);
+int sglm_diff1_f64(const double *X, int64_t ldx, int64_t T, const int32_t *cols, int32_t n_cols, double *out,
+                   int64_t ldo, void *stream);
+int sglm_rolling_minmax_f64(const double *x, int64_t n, const int64_t *seg_lo, const int64_t *seg_hi, int32_t window,
+                            double *out, void *stream);
+
 /* Batched triangular solves with cached factors: out[s] = (L_s L_s')^-1 rhs[s] for every system s with
  * flags[s] == 1 (flags may be NULL); L_of[s] = factor left by sglm_ridge_solve_f64 (work + k (C+1) ldq doubles). */
 int sglm_chol_solve_batched_f64(const double *const *L_of, int64_t ldq, int32_t C, const double *rhs, double *out,

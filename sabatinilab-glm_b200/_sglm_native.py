@@ -89,6 +89,11 @@ _PROTOTYPES = {
                                      c_i32, c_vp, c_vp, c_sz, c_vp]),
     "sglm_pb_state_words": (c_i32, []),
     "sglm_pb_step_f64": (c_i32, [c_vp, c_vp, c_vp]),
+    "sglm_col_moments_workspace_bytes": (c_sz, [c_i64, c_i32]),
+    "sglm_col_moments_f64": (c_i32, [c_vp, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "sglm_zscore_apply_f64": (c_i32, [c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "sglm_diff1_f64": (c_i32, [c_vp, c_i64, c_i64, c_vp, c_i32, c_vp, c_i64, c_vp]),
+    "sglm_rolling_minmax_f64": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_i32, c_vp, c_vp]),
     "sglm_probe_mma_i8": (c_i32, [c_i32, c_vp, c_vp]),
     "sglm_probe_read_f64": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
     "sglm_poisson_irls_prepare_f64": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp,
@@ -148,7 +153,7 @@ def ptr(t):
 # kernels launched per ABI call (for the launch count bench.py reports)
 _KERNELS_PER_CALL = {"sglm_suffstats_f64": 3, "sglm_gram_tc_analyze_f64": 3, "sglm_gram_tc_f64": 3, "sglm_gram_tc_cells_f64": 4, "sglm_gram_tc_cells_partial_f64": 3, "sglm_gram_tc_scaled_f64": 3, "sglm_gram_tc_analyze_scaled_f64": 2, "sglm_xt_vec_f64": 2, "sglm_score_f64": 2, "sglm_poisson_irls_prepare_f64": 2,
                      "sglm_timeshift_f64": 2, "sglm_pb_xt_r_f64": 2, "sglm_pb_epilogue_f64": 2, "sglm_pb_step_f64": 3,
-                     "sglm_lag_valid_rows": 3, "sglm_mask_compact_rows": 3}
+                     "sglm_lag_valid_rows": 3, "sglm_col_moments_f64": 4, "sglm_mask_compact_rows": 3}
 _timing = None         # when enabled: list of (name, start_event, end_event) on the current stream
 
 

@@ -150,6 +150,33 @@ def training_fit_holdout_score(X_setup, y_setup, X_holdout, y_holdout, best_para
     return glm, glm.r2_score(X_holdout, y_holdout), glm.neg_mse_score(X_holdout, y_holdout)
 
 
+def holdout_scores(models, X_holdout, y_holdout):
+    """R^2 and -MSE of MANY fitted Gaussian-family models on one hold-out set in one pass over it — the per-model
+    scoring loop of the drivers (er_refactored_from_scratch_cleanup.py:528-550: `fitted_model.r2_score(X_holdout,
+    y_holdout)` for every model of `full_cv_results`) as batched score-from-statistics: one Gram of [X | y | 1] of
+    the hold-out rows, then RSS_m = v_m' G v_m for all models.  `models`: GLM objects (or anything
+    with coef_ / intercept_).  Returns (r2 [M], neg_mse [M]) numpy arrays equal to the per-model calls."""
+    import torch
+    import _engine as eng
+    Xd, yd = eng.device_matrix(_vals(X_holdout)), eng.device_vector(_vals(y_holdout))
+    T, C = Xd.shape
+    M = len(models)
+    G = eng.suffstats(Xd, yd[:, None].contiguous())[0]
+    ldv = (C + 2 + 1) // 2 * 2
+    V = np.zeros((M, ldv))
+    for i, m in enumerate(models):
+        V[i, :C] = -np.asarray(m.coef_, dtype=np.float64).reshape(-1)
+        V[i, C] = 1.0
+        V[i, C + 1] = -float(np.asarray(m.intercept_).reshape(-1)[0])
+    rss = np.maximum(eng.quadform(G, eng._dev(V, np.float64)).cpu().numpy(), 0.0)
+    mom = G[C:C + 2, C:C + 2].cpu().numpy()                    # [[y'y, sum y], [sum y, n]]
+    n, sy, yy = mom[1, 1], mom[0, 1], mom[0, 0]
+    tss = yy - sy * sy / n
+    with np.errstate(divide='ignore', invalid='ignore'):
+        r2 = np.where(tss <= 0.0, np.where(rss == 0.0, 1.0, 0.0), 1.0 - rss / (tss if tss > 0 else 1.0))
+    return r2, -rss / n
+
+
 def calc_l1(coeffs):
     return np.sum(np.abs(coeffs))
 

@@ -433,11 +433,58 @@ def concat_all_shifts(X, shift_amt_list, shifted_list):
 # CPU passthrough helpers (not kernels; semantics of backend/sglm_pp.py:105-264, :488-545)
 # --------------------------------------------------------------------------- #
 def zscore(X):
+    """(X - mean) / std along axis 0 (backend/sglm_pp.py:105-118).  numpy / pandas input: the reference's expression
+    on the host (numpy std has ddof 0, pandas std ddof 1 and skips NaN).  CUDA tensor input (extension, SURVEY.md
+    §8f-3): the same with numpy's convention on the device (sglm_col_moments_f64 + sglm_zscore_apply_f64)."""
+    if eng.is_torch(X):
+        return zscore_device(X, ddof=0, skipna=False)
     return (X - X.mean(axis=0)) / X.std(axis=0)
 
 
+def zscore_device(X, ddof=0, skipna=False):
+    """z-score the columns of a CUDA tensor; ddof / skipna select numpy (0, False) or pandas (1, True) conventions."""
+    torch = nat.require_cuda()
+    one_d = X.dim() == 1
+    Xd = eng.device_matrix(X)
+    T, C = Xd.shape
+    mean = torch.empty(C, dtype=torch.float64, device="cuda")
+    sd = torch.empty(C, dtype=torch.float64, device="cuda")
+    wb = nat.lib().sglm_col_moments_workspace_bytes(T, C)
+    ws = torch.empty(wb // 8 + 1, dtype=torch.float64, device="cuda")
+    nat.call("sglm_col_moments_f64", nat.ptr(Xd), eng.row_stride(Xd), T, C, int(ddof), int(bool(skipna)), nat.ptr(mean),
+             nat.ptr(sd), nat.ptr(ws), ws.numel() * 8, nat.stream_ptr())
+    out = torch.empty((T, C), dtype=torch.float64, device="cuda")
+    nat.call("sglm_zscore_apply_f64", nat.ptr(Xd), eng.row_stride(Xd), T, C, nat.ptr(mean), nat.ptr(sd), nat.ptr(out), C,
+             nat.stream_ptr())
+    return out[:, 0] if one_d else out
+
+
+def diff_device(X, diff_inx=[], n=1, append_to_base=False, fill_value=np.nan):
+    """n-th difference along axis 0 of the chosen columns of a CUDA tensor (np.diff semantics: n repeated first
+    differences, bit-exact); append_to_base pads n fill rows on top and appends the columns to X as `diff` does."""
+    torch = nat.require_cuda()
+    Xd = eng.device_matrix(X)
+    T, C = Xd.shape
+    cols = [int(c) for c in diff_inx] if len(diff_inx) else list(range(C))
+    cols_d = eng._dev(cols, np.int32)
+    cur, cur_cols = Xd, cols_d
+    for k in range(int(n)):
+        rows = cur.shape[0]
+        nxt = torch.empty((max(rows - 1, 0), len(cols)), dtype=torch.float64, device="cuda")
+        if rows > 1:
+            nat.call("sglm_diff1_f64", nat.ptr(cur), eng.row_stride(cur), rows, nat.ptr(cur_cols) if k == 0 else None,
+                     len(cols), nat.ptr(nxt), len(cols), nat.stream_ptr())
+        cur, cur_cols = nxt, None
+    if not append_to_base:
+        return cur
+    pad = torch.full((int(n), len(cols)), float(fill_value), dtype=torch.float64, device="cuda")
+    return torch.cat([Xd, torch.cat([pad, cur], dim=0)], dim=1)
+
+
 def diff(X, diff_inx=[], n=1, axis=0, append_to_base=False, fill_value=np.nan, **kwargs):
-    """n-th difference of the chosen columns (backend/sglm_pp.py:120-190)."""
+    """n-th difference of the chosen columns (backend/sglm_pp.py:120-190).  CUDA tensors take the device kernel."""
+    if eng.is_torch(X):
+        return diff_device(X, diff_inx, n=n, append_to_base=append_to_base, fill_value=fill_value)
     out_type = type(X)
     if out_type == pd.Series and append_to_base:
         out_type = pd.DataFrame
@@ -529,7 +576,42 @@ def lambda_min_max(X: pd.Series) -> float:
 
 
 def detrend_data(X: pd.DataFrame, detrend_col: str, grouping_cols: List[str], window: int,
-                 standardize: Optional[bool] = False):
-    """Rolling 5-95 % min-max of the centre point (backend/sglm_pp.py:522-545)."""
-    target = X.groupby(grouping_cols)[detrend_col] if grouping_cols else X[detrend_col]
-    return target.rolling(window=window * 2, center=True).apply(lambda_min_max)
+                 standardize: Optional[bool] = False, device=None):
+    """Rolling 5-95 % min-max of the centre point (backend/sglm_pp.py:522-545).  device=True (or
+    SGLM_DEVICE_DESIGN=1): the rolling windows are evaluated on the GPU (sglm_rolling_minmax_f64: one sorted window
+    per position instead of a Python lambda with two pandas quantiles per position) and the same Series comes back
+    (group keys + original index as a MultiIndex when `grouping_cols` is given, exactly as pandas builds it)."""
+    if device is None:
+        device = _device_default()
+    if not device:
+        target = X.groupby(grouping_cols)[detrend_col] if grouping_cols else X[detrend_col]
+        return target.rolling(window=window * 2, center=True).apply(lambda_min_max)
+    return _detrend_device(X, detrend_col, grouping_cols, window)
+
+
+def rolling_minmax_device(x, window, seg_lo=None, seg_hi=None):
+    """The rolling statistic of `detrend_data` for a 1-D CUDA tensor x (window = full window length)."""
+    torch = nat.require_cuda()
+    xd = eng.device_vector(x)
+    out = torch.empty_like(xd)
+    nat.call("sglm_rolling_minmax_f64", nat.ptr(xd), xd.numel(), nat.ptr(seg_lo), nat.ptr(seg_hi), int(window), nat.ptr(out),
+             nat.stream_ptr())
+    return out
+
+
+def _detrend_device(X, detrend_col, grouping_cols, window):
+    vals = np.ascontiguousarray(X[detrend_col].to_numpy(dtype=np.float64))
+    W = int(window) * 2
+    if not grouping_cols:
+        out = rolling_minmax_device(vals, W).cpu().numpy()
+        return pd.Series(out, index=X.index, name=detrend_col)
+    # pandas orders the result by group key, rows of a group in their original order
+    grouped = X.groupby(grouping_cols)[detrend_col]
+    order = np.concatenate([np.asarray(ix) for ix in grouped.indices.values()]) if len(X) else np.zeros(0, np.int64)
+    sizes = [len(ix) for ix in grouped.indices.values()]
+    starts = np.concatenate([[0], np.cumsum(sizes)])
+    seg_lo = np.repeat(starts[:-1], sizes).astype(np.int64)
+    seg_hi = np.repeat(starts[1:], sizes).astype(np.int64)
+    out = rolling_minmax_device(vals[order], W, eng._dev(seg_lo, np.int64), eng._dev(seg_hi, np.int64)).cpu().numpy()
+    ref_index = grouped.rolling(window=2, center=True).count().index       # the MultiIndex pandas builds (cheap)
+    return pd.Series(out, index=ref_index, name=detrend_col)

@@ -269,11 +269,46 @@ def save_by_dict():
     print("by_dict cases:", len(cases))
 
 
+def save_preprocess():
+    """zscore / diff / detrend_data of the reference's preprocessing module (backend/sglm_pp.py:105-190, :522-545) on
+    seeded inputs: ungrouped and grouped (interleaved group rows) rolling min-max, NaNs inside the series."""
+    rng = np.random.default_rng(33)
+    n = 900
+    x = np.cumsum(rng.standard_normal(n)) + 0.01 * np.arange(n)
+    x[[100, 101, 560]] = np.nan
+    grp = rng.integers(0, 3, n)                     # interleaved groups
+    grp2 = (np.arange(n) // 300)                    # contiguous groups
+    df = pd.DataFrame({"sig": x, "g": grp, "h": grp2, "other": rng.standard_normal(n)})
+    blob = {"sig": x, "g": grp, "h": grp2, "other": df["other"].to_numpy()}
+    meta = dict(versions=VERSIONS, cases=[])
+    for i, (cols, window) in enumerate([([], 20), (["g"], 10), (["h"], 25), (["g", "h"], 6)]):
+        out = sglm_pp.detrend_data(df, "sig", cols, window)
+        blob[f"detrend{i}"] = out.to_numpy(dtype=np.float64)
+        idx = out.index.to_frame(index=False).to_numpy() if isinstance(out.index, pd.MultiIndex) else np.asarray(out.index)
+        blob[f"detrend_idx{i}"] = np.asarray(idx, dtype=np.int64)
+        meta["cases"].append(dict(grouping_cols=cols, window=window, index_names=list(out.index.names)))
+    Z = rng.standard_normal((200, 5)) * np.array([1, 10, 0.1, 3, 7]) + np.array([0, 5, -2, 1, 100])
+    blob["Z"] = Z
+    blob["zscore_np"] = sglm_pp.zscore(Z)
+    blob["zscore_df"] = sglm_pp.zscore(pd.DataFrame(Z)).to_numpy()
+    blob["diff1"] = sglm_pp.diff(Z)
+    blob["diff2_cols"] = sglm_pp.diff(Z, diff_inx=[1, 3], n=2)
+    blob["diff1_append"] = sglm_pp.diff(Z, diff_inx=[0, 4], append_to_base=True)
+    np.savez_compressed(os.path.join(OUT, "preprocess_ref.npz"), **blob)
+    with open(os.path.join(OUT, "preprocess_ref.json"), "w") as f:
+        json.dump(meta, f, indent=1)
+    print("preprocess cases:", len(meta["cases"]))
+
+
 if __name__ == "__main__":
+    if "--only-preprocess" in sys.argv:
+        save_preprocess()
+        sys.exit(0)
     if "--only-by-dict" in sys.argv:
         save_by_dict()
         sys.exit(0)
     save_by_dict()
+    save_preprocess()
     save_gather()
     save_fits()
     save_cv()

@@ -416,3 +416,108 @@ def test_poisson_d2_gap_to_the_reference_default_solver():
         assert abs(d2_gpu - d2_default) < 2e-4, (kw, d2_gpu, d2_default)
         assert objective(g.coef_, g.intercept_, kw["alpha"]) <= objective(blob["coefs_default"][i], blob["intercepts_default"][i], kw["alpha"]) + 1e-12
     assert worst > 1e-6          # the gap is real: the default solver does stop early
+
+
+# ------------------------------------------------------------------ steps either side of the path
+def test_preprocess_kernels_vs_reference_golden():
+    """zscore / diff / detrend_data on the device against outputs of the unmodified reference functions
+    (scripts/make_golden.py: backend/sglm_pp.py:105-190, :522-545)."""
+    from conftest import load_golden
+    blob, meta = load_golden("preprocess_ref")
+    Z = torch.from_numpy(blob["Z"]).cuda()
+    assert np.allclose(sglm_pp.zscore(Z).cpu().numpy(), blob["zscore_np"], rtol=1e-12, atol=1e-13)
+    assert np.allclose(sglm_pp.zscore_device(Z, ddof=1, skipna=True).cpu().numpy(), blob["zscore_df"], rtol=1e-12, atol=1e-13)
+    assert sglm_pp.diff(Z).cpu().numpy().tobytes() == blob["diff1"].tobytes()                 # np.diff is bit-exact
+    assert sglm_pp.diff(Z, diff_inx=[1, 3], n=2).cpu().numpy().tobytes() == blob["diff2_cols"].tobytes()
+    got = sglm_pp.diff(Z, diff_inx=[0, 4], append_to_base=True).cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(blob["diff1_append"])) and np.array_equal(np.nan_to_num(got), np.nan_to_num(blob["diff1_append"]))
+    df = pd.DataFrame({"sig": blob["sig"], "g": blob["g"], "h": blob["h"], "other": blob["other"]})
+    for i, case in enumerate(meta["cases"]):
+        out = sglm_pp.detrend_data(df, "sig", case["grouping_cols"], case["window"], device=True)
+        want = blob[f"detrend{i}"]
+        assert out.shape == want.shape
+        assert np.array_equal(np.isnan(out.to_numpy()), np.isnan(want)), case
+        ok = ~np.isnan(want)
+        assert ok.sum() > 100 and np.allclose(out.to_numpy()[ok], want[ok], rtol=1e-10, atol=1e-12), case
+        idx = out.index.to_frame(index=False).to_numpy() if isinstance(out.index, pd.MultiIndex) else np.asarray(out.index)
+        assert np.array_equal(np.asarray(idx, dtype=np.int64), blob[f"detrend_idx{i}"]), case
+        assert list(out.index.names) == case["index_names"]
+        host = sglm_pp.detrend_data(df, "sig", case["grouping_cols"], case["window"])          # reference expression
+        assert np.allclose(host.to_numpy()[ok], want[ok], rtol=1e-12)
+
+
+def test_batched_holdout_scores_equal_per_model_calls():
+    """er_refactored_from_scratch_cleanup.py:528-550 scores every model of the grid on the hold-out set one by one;
+    `sglm_ez.holdout_scores` does it from one Gram of the hold-out rows."""
+    rng = np.random.default_rng(17)
+    n, C = 5000, 40
+    X = rng.standard_normal((n, C)); X[:, 1:] += 0.5 * X[:, :-1]
+    y = X @ (rng.standard_normal(C) * (rng.random(C) < 0.4)) + rng.standard_normal(n)
+    Xh, yh = X[4000:], y[4000:]
+    cv_idx = synth_data.synth_folds(4000, 3, 17, group=100)
+    grid = sglm_cv.generate_mult_params({"alpha": [0.0, 0.01, 0.1], "l1_ratio": [0.0, 0.5, 1.0]}, {"max_iter": 1000})
+    res = sglm_cv.cv_glm_mult_params(X[:4000], y[:4000], cv_idx, "Gaussian", grid, score_method="r2")
+    models = [r["model"] for r in res["full_cv_results"]]
+    r2, nmse = sglm_ez.holdout_scores(models, pd.DataFrame(Xh), pd.Series(yh))
+    for m, a, b in zip(models, r2, nmse):
+        assert abs(m.r2_score(Xh, yh) - a) < 1e-9 and abs(m.neg_mse_score(Xh, yh) - b) < 1e-9
+    glm, hs, hm = sglm_ez.training_fit_holdout_score(pd.DataFrame(X[:4000]), pd.Series(y[:4000]), pd.DataFrame(Xh),
+                                                    pd.Series(yh), dict(res["best_params"]))
+    k = [r["glm_kwargs"] for r in res["full_cv_results"]].index(res["best_params"])
+    assert abs(hs - r2[k]) < 1e-9 and abs(hm - nmse[k]) < 1e-9
+
+
+def test_second_generation_package_and_exporters(tmp_path):
+    """`from sglm.models import ...` (reference sglm/sglm/) resolves to the same kernels; GLM_data pickles and the
+    np.save naming of the drivers round-trip (sglm_save.py:7-68, er_refactored_from_scratch_cleanup.py:528-537)."""
+    import importlib
+    import pickle
+    import subprocess
+    import sys
+    from conftest import PKG
+    code = (
+        "import sys, numpy as np, pandas as pd\n"
+        f"sys.path.insert(0, {repr(PKG + '/gen2')})\n"
+        "from sglm.models import sglm, sglm_cv, split_data, eval as ev, train_model\n"
+        "from sglm.features import sglm_pp, setup_model_fit\n"
+        "from sglm.data import save_results\n"
+        "rng = np.random.default_rng(2)\n"
+        "df = pd.DataFrame({'a': rng.standard_normal(600), 'b': (rng.random(600) < 0.1).astype(float), 'nTrial_filenum': np.arange(600) // 20})\n"
+        "df['y'] = 0.7 * df['a'] - df['b'] + 0.2 * rng.standard_normal(600)\n"
+        "X = sglm_pp.timeshift_cols(df, ['a', 'b'], neg_order=-2, pos_order=2).dropna()\n"
+        "xc = [c for c in X.columns if c not in ('y', 'nTrial_filenum')]\n"
+        "np.random.seed(1)\n"
+        "setup, hold, mask = split_data.holdout_splits(X, id_cols=['nTrial_filenum'], perc_holdout=0.2)\n"
+        "cv = split_data.cv_idx_by_trial_id(setup, trial_id_columns=['nTrial_filenum'], num_folds=3, test_size=0.3)\n"
+        "grid = sglm_cv.generate_mult_params({'alpha': [0.0, 0.1], 'l1_ratio': [0.0, 0.5]}, {'max_iter': 500})\n"
+        "best = sglm_cv.simple_cv_fit(setup[xc], setup['y'], cv, grid, score_method='r2')\n"
+        "g, hs, hm = ev.training_fit_holdout_score(setup[xc], setup['y'], hold[xc], hold['y'], dict(best[2]))\n"
+        "g2 = sglm.fit_GLM(setup[xc], setup['y'], **dict(best[2]))\n"
+        "assert np.array_equal(g.coef_, g2.coef_) and 0.5 < hs <= 1.0\n"
+        "g3 = sglm.GLM('Gaussian', alpha=0.1, l1_ratio=0.5); g3.closed_form = True; g3.fit(setup[xc].values, setup['y'].values)\n"
+        "print('GEN2 OK', len(mask), ev.calc_l1(g.coef_) > 0, ev.calc_l2(g.coef_) > 0)\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "GEN2 OK" in out.stdout, out.stderr[-2000:]
+    import sglm_save
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((300, 6))
+    y = X @ rng.standard_normal(6) + 0.1 * rng.standard_normal(300)
+    cv_idx = synth_data.synth_folds(300, 3, 0, group=20)
+    grid = sglm_cv.generate_mult_params({"alpha": [0.01, 0.1]}, {"l1_ratio": 0.5, "max_iter": 500})
+    res = sglm_cv.cv_glm_mult_params(X, y, cv_idx, "Gaussian", grid, score_method="r2")
+    store = sglm_save.GLM_data(str(tmp_path), "fits.pkl")
+    store.set_uid("run7"); store.set_timeshifts(-2, 2); store.set_X_cols(list("abcdef")); store.set_gss_info(3, 0.2, 0.3)
+    for r in res["full_cv_results"]:
+        store.append_fit_results("y", r["glm_kwargs"], glm_model=r["model"], scores={"gss_witi": r["cv_R2_score"]})
+    store.save()
+    with open(tmp_path / "fits.pkl", "rb") as f:
+        back = pickle.load(f)
+    assert back.data["uid"] == "run7" and len(back.data["fit_results"]) == 2
+    fr = back.data["fit_results"][0]
+    assert set(fr["scores"]) == {"tr_witi", "tr_noiti", "gss_witi", "gss_noiti", "holdout_witi", "holdout_noiti"}
+    assert np.array_equal(fr["glm_model_gss"].coef_, res["full_cv_results"][0]["model"].coef_)
+    paths = sglm_save.save_model_arrays(res, "run7", str(tmp_path / "models"), "coeffs", "intercept")
+    kw = res["full_cv_results"][0]["glm_kwargs"]
+    stem = "run7_" + "_".join(f"{k}_{kw[k]}" for k in kw)
+    assert paths[0][0].endswith(f"/coeffs/{stem}_coeffs.npy") and paths[0][1].endswith(f"/intercepts/{stem}_intercept.npy")
+    assert np.array_equal(np.load(paths[0][0]), res["full_cv_results"][0]["model"].coef_)

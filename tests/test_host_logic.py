@@ -188,3 +188,29 @@ def test_union_of_overlapping_call_intervals():
         assert nat.union_ms(("zzz",)) == 0.0
     finally:
         nat.last_intervals = old
+
+
+def test_exporters_and_gen2_layout_without_gpu(tmp_path):
+    """Result formats (sglm_save.py:7-68; er_refactored_from_scratch_cleanup.py:528-537) and the second-generation
+    package tree need no GPU: pickles of the result container round-trip, file names follow the drivers' rule."""
+    import pickle
+    import sglm_save
+    store = sglm_save.GLM_data(str(tmp_path), "fits.pkl")
+    store.set_uid("u"); store.set_filename("f"); store.set_basedata("b"); store.set_X_cols(["a"]); store.set_timeshifts(-3, 4)
+    store.set_gss_info(5, 0.2, 0.25, gssid=3)
+    store.append_fit_results("resp", {"alpha": 0.1}, glm_model=None, scores={"tr_witi": 0.5}, dropped_cols=["x"], gssids=[1])
+    store.save()
+    store.save()                                     # second save refuses to overwrite, as the reference does
+    with open(tmp_path / "fits.pkl", "rb") as f:
+        back = pickle.load(f)
+    assert back.data["negorder"] == -3 and back.data["posorder"] == 4 and back.data["gss_info"]["gssid"] == 3
+    fr = back.data["fit_results"][0]
+    assert fr["scores"]["tr_witi"] == 0.5 and fr["scores"]["holdout_noiti"] is None and fr["gss_mse"] is None
+    other = sglm_save.GLM_data(str(tmp_path), "fits.pkl")
+    other.load()
+    assert other.data.data["uid"] == "u"             # the reference's load() assigns the unpickled OBJECT to .data
+    assert sglm_save.model_file_stem("r1", {"alpha": 0.5, "l1_ratio": 0.1, "max_iter": 1000}) == "r1_alpha_0.5_l1_ratio_0.1_max_iter_1000"
+    tree = os.path.join(PKG, "gen2", "sglm")
+    for rel in ("models/sglm.py", "models/sglm_cv.py", "models/split_data.py", "models/eval.py", "models/train_model.py",
+                "features/sglm_pp.py", "features/setup_model_fit.py", "data/save_results.py"):
+        assert os.path.exists(os.path.join(tree, rel)), rel
