@@ -680,19 +680,26 @@ def solve_models(models, C, do_screening=True):
     launched = []
     if groups:
         main = torch.cuda.current_stream()
-        ready = torch.cuda.Event()
-        ready.record(main)
         mn_bytes = nat.lib().sglm_ols_minnorm_workspace_bytes(C)
+    # first every buffer and host->device copy (on the main stream: a pageable copy blocks the host until the stream
+    # reaches it, so none may be queued behind a wait on a side stream), then all launches
+    prepared = []
     for gi, idxs in enumerate(groups.values()):
         p = models[idxs[0]].problem
         n_a = len(idxs)
         wb = nat.lib().sglm_ridge_workspace_bytes(C, p.ldq, n_a)
-        # buffers are allocated on the main stream (their allocator pool) and handed to the side stream
         alphas = _dev([0.0 if models[i].kind == "ols" else models[i].alpha for i in idxs], np.float64)
         work = torch.empty(wb // 8, dtype=torch.float64, device="cuda")
         Wr = _empty((n_a, ldw))
         st = torch.empty(n_a, dtype=torch.int32, device="cuda")
-        mn_work = torch.empty(mn_bytes // 8, dtype=torch.float64, device="cuda")
+        has_ols = any(models[i].kind == "ols" for i in idxs)
+        mn_work = torch.empty(mn_bytes // 8, dtype=torch.float64, device="cuda") if has_ols else None
+        prepared.append((idxs, p, n_a, wb, alphas, work, Wr, st, mn_work))
+    if groups:
+        ready = torch.cuda.Event()
+        ready.record(main)
+    side_done = []
+    for gi, (idxs, p, n_a, wb, alphas, work, Wr, st, mn_work) in enumerate(prepared):
         st_ = main if gi == 0 else _side_stream(100 + gi % 8)
         if st_ is not main:
             st_.wait_event(ready)
@@ -700,21 +707,36 @@ def solve_models(models, C, do_screening=True):
             call("sglm_ridge_solve_f64", ptr(p.Qc), p.ldq, ptr(p.qc), C, ptr(alphas), n_a, ptr(Wr), ldw, ptr(st),
                  ptr(work), wb, stream_ptr())
             for k, i in enumerate(idxs):
-                ols = models[i].kind == "ols"
-                call("sglm_ols_minnorm_f64", ptr(p.Qc), p.ldq, ptr(p.qc), C, float(models[i].tol) if ols else 0.0,
-                     0.0 if ols else float(models[i].alpha), 3 if ols else 1, ctypes.c_void_p(st.data_ptr() + 4 * k),
-                     ptr(Wr[k]), ptr(mn_work), mn_bytes, stream_ptr())
+                # least squares (alpha == 0): rank deficiency is decided on the device — the launch returns at once
+                # when every pivot was healthy.  (Ridge systems are positive definite; a failed one is re-solved
+                # after the status read-back below, as scikit-learn falls back to its SVD solver.)
+                if models[i].kind == "ols":
+                    call("sglm_ols_minnorm_f64", ptr(p.Qc), p.ldq, ptr(p.qc), C, float(models[i].tol), 0.0, 3,
+                         ctypes.c_void_p(st.data_ptr() + 4 * k), ptr(Wr[k]), ptr(mn_work), mn_bytes, stream_ptr())
             if st_ is not main:
                 ev = torch.cuda.Event()
                 ev.record(st_)
-                main.wait_event(ev)
+                side_done.append(ev)
                 for t in (alphas, work, Wr, st, mn_work):
-                    t.record_stream(st_)
-        launched.append((idxs, Wr, st))
-    for idxs, Wr, st in launched:
+                    if t is not None:
+                        t.record_stream(st_)
+        launched.append((idxs, Wr, st, p, mn_work))
+    for ev in side_done:
+        main.wait_event(ev)
+    for idxs, Wr, st, p, mn_work in launched:
+        st_h = st.cpu().numpy()
+        for k, i in enumerate(idxs):
+            if (st_h[k] & 1) and models[i].kind == "ridge":
+                # Cholesky met a non-positive pivot: the spectral solve, as sklearn's SVD fallback (_ridge.py:_solve_svd)
+                if mn_work is None:
+                    mn_work = torch.empty(mn_bytes // 8, dtype=torch.float64, device="cuda")
+                call("sglm_ols_minnorm_f64", ptr(p.Qc), p.ldq, ptr(p.qc), C, 0.0, float(models[i].alpha), 1,
+                     ctypes.c_void_p(st.data_ptr() + 4 * k), ptr(Wr[k]), ptr(mn_work), mn_bytes, stream_ptr())
+        if np.any(st_h & 1):
+            st_h = st.cpu().numpy()
         W.index_copy_(0, _dev(idxs, np.int64), Wr)
         # bit 1 alone (a tiny but positive pivot of a Ridge system) is not an error; bit 0 is cleared by the fallback
-        status[idxs] = (st.cpu().numpy() & 1) * 2                     # 2 = not positive definite and not recovered
+        status[idxs] = (st_h & 1) * 2                                 # 2 = not positive definite and not recovered
     del launched
     return W, info, status
 
@@ -1056,7 +1078,8 @@ def _poisson_batch(Xd, Yd, models, RW):
     f64, i32 = np.float64, np.int32
     W, Wprev, Wnew, rhs = (_zeros((B, ldw)) for _ in range(4))
     b = _dev(b0, f64)
-    bprev, fprev, fcur, last_step, step_out, ratio_out = (_zeros((B,)) for _ in range(6))
+    bprev, fprev, fcur, last_step, step_out = (_zeros((B,)) for _ in range(5))
+    ratio_out = torch.ones(B, dtype=torch.float64, device="cuda")        # 1.0 = contraction not known yet
     zi = lambda: torch.zeros(B, dtype=torch.int32, device="cuda")
     halv, n_iter, status, flag, has_prev = zi(), zi(), zi(), zi(), zi()
     alpha = _dev([m.alpha for m in models], f64)
@@ -1109,7 +1132,9 @@ def _poisson_batch(Xd, Yd, models, RW):
         Hh11[g:g + 1] = h11
         stride = (C + 1) * hess.ldq * 8
         L_of[_dev(idxs, np.int64)] = _dev([work.data_ptr() + k * stride for k in range(len(idxs))], np.int64)
-        last_step[_dev(idxs, np.int64)] = 0.0     # the contraction estimate restarts with the new Hessian
+        sel = _dev(idxs, np.int64)
+        last_step[sel] = 0.0                      # the contraction estimate restarts with the new Hessian
+        ratio_out[sel] = 1.0
 
     for g in range(n_h):
         refresh(g, groups[gkeys[g]][0])
@@ -1177,9 +1202,11 @@ def poisson_scores_batched(Xd, Yd, W, b, ycol, rw_a, rw_b, RW):
         sums = _zeros((n, 16))
         ep_bytes = nat.lib().sglm_pb_epilogue_workspace_bytes(T, n)
         ep_ws = torch.empty(ep_bytes // 8 + 1, dtype=torch.float64, device="cuda")
-        call("sglm_pb_epilogue_f64", ptr(Eta), ldb, n, T, ptr(Yd), Yd.stride(0), ptr(_dev(ycol[c0:c0 + n], np.int32)),
+        # named tensors: a temporary freed inside the argument list would hand its block to the next allocation
+        ids = _dev(np.stack([ycol[c0:c0 + n], rw_a[c0:c0 + n], rw_b[c0:c0 + n]]), np.int32)
+        b_part = b[c0:c0 + n].contiguous()
+        call("sglm_pb_epilogue_f64", ptr(Eta), ldb, n, T, ptr(Yd), Yd.stride(0), ptr(ids[0]),
              ptr(RW) if RW is not None else None, RW.stride(0) if RW is not None else 0,
-             ptr(_dev(rw_a[c0:c0 + n], np.int32)), ptr(_dev(rw_b[c0:c0 + n], np.int32)), ptr(b[c0:c0 + n].contiguous()),
-             None, 1, ptr(sums), ptr(ep_ws), ep_ws.numel() * 8, stream_ptr())
+             ptr(ids[1]), ptr(ids[2]), ptr(b_part), None, 1, ptr(sums), ptr(ep_ws), ep_ws.numel() * 8, stream_ptr())
         out[c0:c0 + n] = sums.cpu().numpy().reshape(n, 2, 8)
     return out

@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(256)
 pb_finish_kernel(PbState s) {
     __shared__ double sh[8];
     const int m = blockIdx.x, tid = threadIdx.x;
-    if (s.flag[m] != 1) { if (tid == 0) { s.step_out[m] = s.flag[m] == 2 ? -1.0 : 0.0; s.ratio_out[m] = 0.0; } return; }
+    if (s.flag[m] != 1) { if (tid == 0) s.step_out[m] = s.flag[m] == 2 ? -1.0 : 0.0; return; }
     double *w = s.W + (long long)m * s.ldw, *wp = s.Wprev + (long long)m * s.ldw;
     const double *wn = s.Wnew + (long long)m * s.ldw;
     const int h = s.hess_id[m];
@@ -358,14 +358,17 @@ pb_finish_kernel(PbState s) {
         const double step = fmax(dw, fabs(b_new - b_old)) / fmax(1.0, wmax);
         const double last = s.last_step[m];
         const bool have = last > 0.0 && last < 1e300;
-        const double rho = have ? fmin(step / last, 0.9) : 1.0;
+        const double ratio = have ? step / last : 1.0;
+        // contraction estimate = the worse of the last two ratios (1.0 = not known yet: the first two steps after a
+        // Hessian refresh cannot declare convergence unless the step itself is below the target)
+        const double rho = fmin(fmax(ratio, s.ratio_out[m]), 0.9);
         s.bprev[m] = b_old; s.b[m] = b_new; s.fprev[m] = s.fcur[m]; s.has_prev[m] = 1;
         s.n_iter[m] += 1;
         // linear convergence (inexact Hessian): after a step that contracted by rho the iterate is within
         // step * rho / (1 - rho) of the optimum
-        if (step * rho / (1.0 - fmin(rho, 0.9)) <= fmin(s.tol[m], 1e-8) || step <= 1e-12) s.status[m] = 1;
+        if (step * rho / (1.0 - rho) <= fmin(s.tol[m], 1e-8) || step <= 1e-12) s.status[m] = 1;
         s.step_out[m] = step;
-        s.ratio_out[m] = have ? step / last : 1.0;
+        s.ratio_out[m] = ratio;
         s.last_step[m] = step;
     }
 }

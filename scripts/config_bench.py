@@ -86,11 +86,15 @@ def run_c1(cpu):
 
     def dev():
         d = sglm_pp.timeshift_multiple(X0, shift_amt_list=shifts)[lo:hi]
-        return sglm.GLM("Gaussian", alpha=0.01, l1_ratio=0.5).fit(d, y)
+        g = sglm.GLM("Gaussian", alpha=0.01, l1_ratio=0.5)
+        g.fit(d, y)
+        return g
 
     def e2e():
         d = sglm_pp.timeshift_multiple(X0_h, shift_amt_list=shifts, device=True).dropna()
-        return sglm.GLM("Gaussian", alpha=0.01, l1_ratio=0.5).fit(d, y_h)
+        g = sglm.GLM("Gaussian", alpha=0.01, l1_ratio=0.5)
+        g.fit(d, y_h)
+        return g
     sec, _, per = timed(dev)
     sec_e, g, _ = timed(e2e)
     line = {"config": "c1 (BASELINE configs[0]): single Gaussian ElasticNet fit (alpha 0.01, l1_ratio 0.5), 100k timepoints x "
@@ -149,7 +153,7 @@ def run_c4(cpu):
     folds_h = synth_data.synth_folds(n, 5, 4)
     folds = [(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()) for a, b in folds_h]
     y_h = y.cpu().numpy()
-    grid = [dict(alpha=float(a)) for a in np.logspace(-4, 1, 20)]
+    grid = [dict(alpha=float(a), model_name="Poisson") for a in np.logspace(-4, 1, 20)]      # backend/sglm_cv.py:288
     d_keep = sglm_pp.timeshift_multiple(X0, shift_amt_list=shifts)[lo:hi]
 
     def dev():

@@ -362,7 +362,10 @@ def test_poisson_batched_grid_vs_oracle_and_sklearn():
     assert Xd.shape[1] == 800
     y = synth_data.synth_response(Xd, synth_data.synth_kernels(P, shifts, 404), 404, poisson=True)
     cv_idx = synth_data.synth_folds(Xd.shape[0], 3, 404, group=500)
-    grid = [dict(alpha=a) for a in (1e-3, 1e-2, 0.1, 1.0)] + [dict(alpha=0.05, fit_intercept=False), dict(alpha=0.02, roll=5)]
+    # the family travels INSIDE the parameter sets: cv_glm_mult_params pops `model_name` with default 'Gaussian' and
+    # ignores its own argument (backend/sglm_cv.py:288)
+    grid = [dict(alpha=a, model_name="Poisson") for a in (1e-3, 1e-2, 0.1, 1.0)] + [
+        dict(alpha=0.05, fit_intercept=False, model_name="Poisson"), dict(alpha=0.02, roll=5, model_name="Poisson")]
     want = orc.cv_glm_mult_params(Xd, y, cv_idx, "Poisson", [dict(k) for k in grid], score_method="r2")
     old = eng.POISSON_TC
     try:
