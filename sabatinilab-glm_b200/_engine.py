@@ -514,11 +514,18 @@ def _cd_plan(C, n_models):
 
 
 def _CD_DEFAULT_PLAN(C, n_models):
-    # wide designs: the heaviest 30 % of the cost-ordered grid as groups of 4 models of one fold on 2-CTA
-    # clusters, the light rest concurrently on the one-CTA-per-model kernel (measured best,
-    # profiles/r1_cd_cluster.txt).  A handful of models (a single GLM.fit) leaves the GPU idle anyway: each
-    # model gets a 4-CTA cluster (config 1: CD 5.6 -> 4.3 ms).  Narrow designs keep one CTA per model.
+    # wide designs: the heaviest 30 % of the cost-ordered grid as groups of M models of one fold on K-CTA clusters,
+    # the light rest concurrently on the one-CTA-per-model kernel.  A model is a serial chain of 32-coordinate
+    # blocks; measured per block for the heaviest model (profiles/r2_cd_experiments.txt): 6.1 us on (4,2), 4.75 us
+    # on (4,4), 4.15 us on (2,4) — wider clusters shorten the chain but need more SMs per model, so the shape follows
+    # the number of models this GPU holds (a whole grid: (4,2); a share of a grid dealt over several GPUs: wider).
+    # A handful of models (a single GLM.fit) leaves the GPU idle anyway: each model gets a 4-CTA cluster
+    # (config 1: CD 5.6 -> 4.3 ms).  Narrow designs keep one CTA per model.
     if C > 1024 and n_models >= 16:
+        heavy = 0.3 * n_models
+        for m, k, sm_budget in ((2, 4, 160), (4, 4, 240)):
+            if -(-heavy // m) * k <= sm_budget:
+                return f"{m}x{k}@0.3,0x0"
         return "4x2@0.3,0x0"
     if C >= 256 and n_models <= 8:
         return "1x4"

@@ -792,6 +792,10 @@ static int launch_sized(const Args &a) {
     switch (a.variant) {
         case 1: return launch_a<M, K, 8, 1, 4, 1>(a);
         case 2: return launch_a<M, K, 8, 2, 2, 2>(a);
+        // 16-warp CTA: the M register warps share ONE SM sub-partition (warp ids 0, 4, 8, 12), 12 panel warps own the
+        // other three — the register chains no longer queue behind the panel's FP64 FMAs in their scheduler
+        case 6: return launch_a<M, K, 12, 1, 4, 1>(a);
+        case 7: return launch_a<M, K, 12, 1, 8, 1>(a);
         default: break;
     }
     if (own2 <= 128) return launch_a<M, K, 4, 1, 8, 1>(a);

@@ -235,8 +235,9 @@ def cv_grid_strong(X0, shift_amt_list, y, cv_idx, model_name, glm_kwarg_lst, ver
     mark("start")
     shifts = [int(a) for a in shift_amt_list]
     smax, smin = max(0, max(shifts)), min(0, min(shifts))
-    # ---- source rank: inputs to the device, fold checks
-    meta = [None]
+    # ---- source rank: inputs to the device, fold checks; the shapes travel as one small int64 header
+    HDR = 72                                                          # T, P, lo, hi, F, ok, then up to 64 fold sizes
+    hdr = torch.zeros(HDR, dtype=torch.int64, device=dev)
     if rank == src:
         X0d = eng.device_matrix(X0)
         T, P = X0d.shape
@@ -247,17 +248,21 @@ def cv_grid_strong(X0, shift_amt_list, y, cv_idx, model_name, glm_kwarg_lst, ver
             raise ValueError(f"Found input variables with inconsistent numbers of samples: [{n}, {yd.numel()}]")
         cv = sglm_cv._normalise_cv_idx(list(cv_idx), n)
         tests = sglm_cv._unique_sorted_rows(cv, n)
-        ok = tests is not None and all(len(tr) + len(te) == n for tr, te in cv)
+        ok = tests is not None and len(cv) <= HDR - 8 and all(len(tr) + len(te) == n for tr, te in cv)
         if ok:
             _, _, _, _, comp = sglm_cv._fold_weights(cv, n)
             ok = bool(np.all(comp))
-        meta = [dict(T=T, P=P, lo=lo, hi=hi, n_te=[int(t.numel()) for t in tests] if ok else None, ok=ok)]
-    dist.broadcast_object_list(meta, src=src, group=group)
-    m = meta[0]
-    if not m["ok"]:
-        raise NotImplementedError("cv_grid_strong needs complement train/test folds with duplicate-free test rows")
-    T, P, lo, hi, n_te = m["T"], m["P"], m["lo"], m["hi"], m["n_te"]
-    n, F = hi - lo, len(n_te)
+        head = [T, P, lo, hi, len(cv), int(ok)] + ([int(t.numel()) for t in tests] if ok else [])
+        hdr[:len(head)] = torch.tensor(head, dtype=torch.int64)
+    mark("prepare")
+    dist.broadcast(hdr, src=src, group=group)
+    h = hdr.cpu().numpy()
+    if not h[5]:
+        raise NotImplementedError("cv_grid_strong needs complement train/test folds with duplicate-free test rows "
+                                  "(at most 64 folds)")
+    T, P, lo, hi, F = (int(v) for v in h[:5])
+    n_te = [int(v) for v in h[6:6 + F]]
+    n = hi - lo
     if rank != src:
         X0d = torch.empty((T, P), dtype=torch.float64, device=dev)
         yd = torch.empty(n, dtype=torch.float64, device=dev)
