@@ -61,6 +61,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="grid", choices=["grid", "sessions"])
+    ap.add_argument("--sessions-per-gpu", type=int, default=1,
+                    help="sessions mode: independent sessions batched into one launch plan per GPU (BASELINE configs[4]: "
+                         "64 sessions on 8 GPUs = 8 per GPU at --T 250000)")
     ap.add_argument("--T", type=int, default=2_000_000)
     ap.add_argument("--P", type=int, default=40)
     ap.add_argument("--shift-lo", type=int, default=-20)
@@ -103,8 +106,9 @@ def make_session(args, seed, T):
 def config_dict(args, n_gpus, mode):
     shifts, grid = workload(args)
     C = args.P * len(shifts)
+    spg = getattr(args, "sessions_per_gpu", 1)
     layout = ("ONE grid strong-scaled over the GPUs (row-sharded Gram + models dealt by cost)" if mode == "grid"
-              else "one independent session per GPU")
+              else f"{spg} independent session(s) per GPU, batched into one launch plan per GPU (BASELINE.json configs[4])")
     return {"workload": f"ElasticNet CV grid {args.folds} folds x {args.alphas} alphas x {args.l1s} l1_ratios "
                         f"(+1 full-data refit per set = {len(grid) * (args.folds + 1)} fits/step) on "
                         f"{args.T} timepoints x {C} lagged columns (P={args.P} base signals x {len(shifts)} shifts), "
@@ -113,7 +117,7 @@ def config_dict(args, n_gpus, mode):
                         f"(BASELINE.json configs[2]); {layout}",
             "T": args.T, "C": C, "folds": args.folds, "alphas": args.alphas, "l1_ratios": args.l1s,
             "fits_per_step": len(grid) * (args.folds + 1), "mode": mode,
-            "sessions": n_gpus if mode == "sessions" else 1,
+            "sessions": n_gpus * spg if mode == "sessions" else 1,
             "l2_policy": "inputs larger than L2 (design matrix %.1f GB >> 126 MB)" % (args.T * C * 8 / 1e9)}
 
 
@@ -330,6 +334,20 @@ def main():
     folds_np = [(a.numpy(), b.numpy()) for a, b in folds_pin]
     torch.cuda.synchronize()
 
+    extra_sessions = []
+    if mode == "sessions" and args.sessions_per_gpu > 1:
+        # BASELINE configs[4]: several independent sessions per GPU, all their models in one launch plan
+        def one_session(seed_i):
+            X0_i, beta_i, _, folds_i = make_session(args, seed_i, args.T)
+            X0_di = torch.from_numpy(X0_i).cuda()
+            Xi = sglm_pp.timeshift_multiple(X0_di, shift_amt_list=shifts)[h_lo: args.T - h_hi]
+            si = Xi @ torch.from_numpy(beta_i).cuda()
+            gi = torch.Generator(device="cuda").manual_seed(seed_i)
+            yi = si + float(si.std()) * float(np.sqrt(0.7 / 0.3)) * torch.randn(si.shape, dtype=torch.float64, device="cuda", generator=gi)
+            yi = ((yi - yi.mean()) / yi.std()).contiguous()
+            return X0_di, yi, [(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()) for a, b in folds_i]
+        extra_sessions = [one_session(5000 + rank * args.sessions_per_gpu + i) for i in range(1, args.sessions_per_gpu)]
+
     if strong:
         import sglm_dist
 
@@ -342,6 +360,12 @@ def main():
             return sglm_dist.cv_grid_strong(X0_np if rank == 0 else None, shifts, y_np if rank == 0 else None,
                                             folds_np if rank == 0 else None, "Gaussian", [dict(g) for g in grid],
                                             score_method="r2", rows=(h_lo, args.T - h_hi))
+    elif extra_sessions:
+        def step_device():
+            ses = [(sglm_pp.timeshift_multiple(x0, shift_amt_list=shifts)[h_lo: args.T - h_hi], yy, ff)
+                   for x0, yy, ff in [(X0_d, y_d, folds_d)] + extra_sessions]
+            return sglm_cv.cv_glm_mult_params_sessions(ses, "Gaussian", [dict(g) for g in grid], score_method="r2")[0]
+        step_e2e = None
     else:
         def step_device():
             d = sglm_pp.timeshift_multiple(X0_d, shift_amt_list=shifts)
@@ -392,7 +416,7 @@ def main():
     nat.enable_timing(False)
     launches = nat.launches() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    n_sessions = world if mode == "sessions" else 1
+    n_sessions = world * args.sessions_per_gpu if mode == "sessions" else 1
     value = fits_per_step * args.steps * n_sessions / (total_ms / 1e3)
 
     # ---- per-kernel accounting for the roofline of the dominant kernel (rank 0's launches)
@@ -508,7 +532,7 @@ def main():
 
     # ---- end to end through the reference-facing API from host (numpy) buffers
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and step_e2e is not None:
         step_e2e()
         e2e_steps = max(1, min(args.steps, 2))
         e2e_ms, res_e = timed(step_e2e, e2e_steps)

@@ -528,8 +528,10 @@ enet_cd_cluster_kernel(const double *const *__restrict__ prob_Q, const double *c
                     // Candidates of all 32 lanes from the current state; lanes whose candidate is zero need no
                     // turn (see solvers.cu): dense blocks run the straight 32-step chain, sparse ones jump from
                     // mover to mover.
+                    // r = (q + w d) - Qw carried directly (see solvers.cu): one FMA per step on the dependent chain
+                    double r_l = a_l - Qw_l;
                     auto candidate = [&]() -> double {
-                        const double rr = a_l - Qw_l;
+                        const double rr = r_l;
                         const double dpos = fma(rr, inv_l, k_pos), dneg = fma(rr, inv_l, k_neg);
                         return (rr > l1) ? dpos : ((rr < -l1) ? dneg : negw);
                     };
@@ -542,7 +544,7 @@ enet_cd_cluster_kernel(const double *const *__restrict__ prob_Q, const double *c
                             const double dc = candidate();
                             const double di = __shfl_sync(0xffffffffu, dc, i);
                             if (lane == i) delta_l = dc;
-                            Qw_l = fma(di, s_il, Qw_l);
+                            r_l = fma(-di, s_il, r_l);
                         }
                     } else {
                         double dc = candidate();
@@ -553,7 +555,7 @@ enet_cd_cluster_kernel(const double *const *__restrict__ prob_Q, const double *c
                             const int i = __ffs(mv) - 1;
                             const double di = __shfl_sync(0xffffffffu, dc, i);
                             if (lane == i) delta_l = dc;
-                            Qw_l = fma(di, S[i * 32 + lane], Qw_l);
+                            r_l = fma(-di, S[i * 32 + lane], r_l);
                             todo &= ~((2u << i) - 1u);                    // coordinates up to i have had their turn
                             if (!todo) break;
                             dc = candidate();

@@ -301,7 +301,7 @@ enet_cd_gram_kernel(const double *const *__restrict__ prob_Q, const double *cons
                 const double d_l = inb ? qd[buf * 64 + 32 + lane] : 0.0;
                 const double inv_l = (d_l != 0.0) ? 1.0 / (d_l + l2) : 1.0;
                 const bool ok_l = ((mask >> lane) & 1u) && d_l != 0.0;
-                double Qw_l = inb ? Qw[j_l] : 0.0;
+                const double Qw_l = inb ? Qw[j_l] : 0.0;
                 const double w_l = inb ? w[j_l] : 0.0;
                 // Soft-threshold update written for a short dependent chain (the 32 steps are
                 // serialised through Qw_l):  with r = (q + w d) - Qw,
@@ -315,8 +315,12 @@ enet_cd_gram_kernel(const double *const *__restrict__ prob_Q, const double *cons
                 // sweep jumps to the first lane (in coordinate order) whose candidate is non-zero, applies it
                 // exactly as the sequential algorithm would, and re-evaluates the lanes after it.  A sparse
                 // model pays for the coordinates that move, not for 32 serial steps per block.
+                // r = (q + w d) - Qw is carried directly: an update of Qw by +delta_i S_il is r -= delta_i S_il, one FMA
+                // on the dependent chain instead of an FMA followed by a subtraction (the chain of 32 serial steps
+                // per block is what bounds the heaviest models)
+                double r_l = a_l - Qw_l;
                 auto candidate = [&]() -> double {
-                    const double r = a_l - Qw_l;
+                    const double r = r_l;
                     const double dpos = fma(r, inv_l, k_pos), dneg = fma(r, inv_l, k_neg);
                     const double dc = (r > l1) ? dpos : ((r < -l1) ? dneg : -w_l);
                     return ok_l ? dc : 0.0;
@@ -331,7 +335,7 @@ enet_cd_gram_kernel(const double *const *__restrict__ prob_Q, const double *cons
                         const double dc = candidate();
                         const double di = __shfl_sync(0xffffffffu, dc, i);
                         if (lane == i) delta_l = dc;
-                        Qw_l = fma(di, s_il, Qw_l);
+                        r_l = fma(-di, s_il, r_l);
                     }
                 } else {
                     double dc = candidate();
@@ -342,7 +346,7 @@ enet_cd_gram_kernel(const double *const *__restrict__ prob_Q, const double *cons
                         const int i = __ffs(mv) - 1;
                         const double di = __shfl_sync(0xffffffffu, dc, i);
                         if (lane == i) delta_l = dc;
-                        Qw_l = fma(di, inb ? S[i * 32 + lane] : 0.0, Qw_l);
+                        r_l = fma(-di, inb ? S[i * 32 + lane] : 0.0, r_l);
                         todo &= ~((2u << i) - 1u);                        // coordinates up to i have had their turn
                         if (!todo) break;
                         dc = candidate();

@@ -78,10 +78,11 @@ def _normalise_cv_idx(cv_idx, T):
                                          f"but size of corresponding boolean axis is {a.shape[0]}")
                     a = np.flatnonzero(a)
                 a = a.astype(np.int64, copy=False)
-                if a.size and (a.min() < -T or a.max() >= T):
+                lo_, hi_ = (int(a.min()), int(a.max())) if a.size else (0, 0)
+                if lo_ < -T or hi_ >= T:
                     bad = a[(a < -T) | (a >= T)][0]
                     raise IndexError(f"index {int(bad)} is out of bounds for axis 0 with size {T}")
-                norm.append(np.where(a < 0, a + T, a))
+                norm.append(np.where(a < 0, a + T, a) if lo_ < 0 else a)       # the usual lists need no wrap
         out.append(tuple(norm))
     if checks and bool(torch.stack(checks).any().item()):
         raise IndexError(f"index out of bounds for axis 0 with size {T}")
