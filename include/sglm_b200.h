@@ -87,6 +87,16 @@ int sglm_lag_valid_rows(const double *X, int64_t T, int32_t n_cols_in, int64_t l
  * aligned): mask[t] = 1 for listed rows, *dup_flag = 1 when a row is listed twice.  With mask_compact_rows this
  * gives the sorted, duplicate-free test rows of a fold (backend/sglm_cv.py:106-110) without a sort. */
 int sglm_index_mask_u8(const int64_t *idx, int64_t n_idx, uint8_t *mask, int64_t T, int32_t *dup_flag, void *stream);
+/* Disjoint cells of overlapping row sets (the full data contain every test fold; random folds intersect —
+ * GroupShuffleSplit, backend/sglm_pp.py:262-263) without a sort:
+ *   rows_or_bit          : sig[t] |= 1 << bit for the rows listed in set `bit` (sig zeroed by the caller, <= 62 sets);
+ *   cells_from_signatures: distinct signatures -> cell ids; `table` (device, 4104 bytes) = 256 keys (uint64, ~0 = empty
+ *                          slot), 256 row counts (int64), {slots used, overflow flag} (int32); cell_of[t] = slot;
+ *   match_compact_rows   : ascending rows of one cell (rows whose byte equals `match`). */
+int sglm_rows_or_bit_u64(const int64_t *idx, int64_t n_idx, int32_t bit, uint64_t *sig, int64_t T, void *stream);
+int sglm_cells_from_signatures(const uint64_t *sig, int64_t T, uint8_t *cell_of, void *table, void *stream);
+int sglm_match_compact_rows(const uint8_t *ids, int64_t T, int32_t match, int64_t *rows, void *workspace,
+                            size_t workspace_bytes, void *stream);
 /* np.roll(y, shift) (the `roll` key of a parameter set, backend/sglm_cv.py:95-96): out[(i + shift) mod n] = y[i]. */
 int sglm_roll_f64(const double *y, int64_t n, int64_t shift, double *out, void *stream);
 size_t sglm_mask_compact_workspace_bytes(int64_t T);

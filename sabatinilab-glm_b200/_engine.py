@@ -352,28 +352,39 @@ def _row_cells(set_rows, T):
     if not listed or len(listed) > 60 or len(set_rows) < 2:
         return None
     any_all = len(listed) < len(set_rows)
-    sig = torch.zeros(T, dtype=torch.int64, device="cuda")
+    # row signatures (bit b = row is in listed set b), distinct signatures = cells: a 256-slot hash table on the
+    # device, one read-back of the table (keys + counts), then one ordered compaction per cell — no sort
+    sig = torch.zeros(max(T, 1), dtype=torch.int64, device="cuda")
     for bit, i in enumerate(listed):
-        sig[set_rows[i].to(torch.int64)] += (1 << bit)
-    order = torch.argsort(sig, stable=True)
-    uniq, counts = torch.unique_consecutive(sig[order], return_counts=True)
-    if uniq.numel() > _MAX_CELLS + 1:
+        r = set_rows[i].to(torch.int64)
+        call("sglm_rows_or_bit_u64", ptr(r), r.numel(), bit, ptr(sig), T, stream_ptr())
+    cell_of = torch.empty(max(T, 1), dtype=torch.uint8, device="cuda")
+    table = torch.empty(513 + 1, dtype=torch.int64, device="cuda")
+    call("sglm_cells_from_signatures", ptr(sig), T, ptr(cell_of), ptr(table), stream_ptr())
+    th = table.cpu().numpy()
+    keys_h, counts_h, flags = th[:256], th[256:512], th[512:513].view(np.int32)
+    if flags[1] != 0:
         return None
-    host = torch.stack([uniq, counts]).cpu().numpy()
-    uniq_h, counts_h = host[0], host[1]
+    slots = [int(sl) for sl in np.flatnonzero(counts_h > 0)]
+    slots.sort(key=lambda sl: int(keys_h[sl]) & 0xFFFFFFFFFFFFFFFF)           # ascending signature: a fixed cell order
+    if len(slots) > _MAX_CELLS + 1:
+        return None
     total_listed = sum(int(set_rows[i].numel()) for i in listed) + (T if any_all else 0) * (len(set_rows) - len(listed))
-    cell_rows = int(counts_h.sum()) if any_all else int(counts_h[uniq_h != 0].sum())
+    cell_rows = sum(int(counts_h[sl]) for sl in slots if any_all or keys_h[sl] != 0)
     if cell_rows >= total_listed:             # disjoint sets: nothing to share
         return None
     lists, member_cols = [], []
-    start = 0
     bit_of = {i: b for b, i in enumerate(listed)}
-    for u, n in zip(uniq_h, counts_h):
-        n = int(n)
-        if u != 0 or any_all:
-            lists.append(order[start:start + n])
-            member_cols.append([1 if r is None else int((int(u) >> bit_of[i]) & 1) for i, r in enumerate(set_rows)])
-        start += n
+    wb = nat.lib().sglm_mask_compact_workspace_bytes(T)
+    ws = torch.empty((wb + 7) // 8, dtype=torch.int64, device="cuda")
+    for sl in slots:
+        u = int(keys_h[sl])
+        if u == 0 and not any_all:
+            continue
+        rows_c = torch.empty(int(counts_h[sl]), dtype=torch.int64, device="cuda")
+        call("sglm_match_compact_rows", ptr(cell_of), T, sl, ptr(rows_c), ptr(ws), ws.numel() * 8, stream_ptr())
+        lists.append(rows_c)
+        member_cols.append([1 if r is None else int((u >> bit_of[i]) & 1) for i, r in enumerate(set_rows)])
     member = np.array(member_cols, dtype=np.int32).T          # [n_sets][n_cells]
     return lists, member
 

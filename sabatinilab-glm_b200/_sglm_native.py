@@ -25,6 +25,9 @@ _PROTOTYPES = {
                                           c_u64, c_vp, c_i64, c_vp]),
     "sglm_lag_valid_rows": (c_i32, [c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "sglm_index_mask_u8": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
+    "sglm_rows_or_bit_u64": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i64, c_vp]),
+    "sglm_cells_from_signatures": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "sglm_match_compact_rows": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp, c_sz, c_vp]),
     "sglm_roll_f64": (c_i32, [c_vp, c_i64, c_i64, c_vp, c_vp]),
     "sglm_mask_compact_workspace_bytes": (c_sz, [c_i64]),
     "sglm_mask_compact_rows": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),

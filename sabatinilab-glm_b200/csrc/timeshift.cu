@@ -184,11 +184,14 @@ mask_summary_kernel(const unsigned char *__restrict__ valid, long long T, long l
 // Ordered compaction of the set rows of a mask: block b owns rows [b*CH, (b+1)*CH); pass A counts, a one-block
 // exclusive scan of the block counts follows, pass B writes the row indices in ascending order.
 constexpr int CMP_CH = 4096;
+// match < 0: a row is selected when its byte is non-zero; match >= 0: when its byte equals `match` (cell ids)
+__device__ __forceinline__ bool mask_hit(unsigned char v, int match) { return match < 0 ? (v != 0) : ((int)v == match); }
+
 __global__ void __launch_bounds__(256)
-mask_block_count_kernel(const unsigned char *__restrict__ valid, long long T, long long *__restrict__ counts) {
+mask_block_count_kernel(const unsigned char *__restrict__ valid, long long T, int match, long long *__restrict__ counts) {
     const long long t0 = (long long)blockIdx.x * CMP_CH;
     int c = 0;
-    for (int i = threadIdx.x; i < CMP_CH; i += 256) c += (t0 + i < T && valid[t0 + i]) ? 1 : 0;
+    for (int i = threadIdx.x; i < CMP_CH; i += 256) c += (t0 + i < T && mask_hit(valid[t0 + i], match)) ? 1 : 0;
     __shared__ int sh[8];
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
@@ -220,7 +223,7 @@ exclusive_scan_kernel(long long *__restrict__ counts, long long n) {
     }
 }
 __global__ void __launch_bounds__(256)
-mask_compact_kernel(const unsigned char *__restrict__ valid, long long T, const long long *__restrict__ offs,
+mask_compact_kernel(const unsigned char *__restrict__ valid, long long T, int match, const long long *__restrict__ offs,
                     long long *__restrict__ rows) {
     // a warp owns 512 consecutive rows of the block's 4096 (ballot-ordered writes); warp prefix via shared memory
     const long long t0 = (long long)blockIdx.x * CMP_CH;
@@ -231,7 +234,7 @@ mask_compact_kernel(const unsigned char *__restrict__ valid, long long T, const 
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
         const long long t = t0 + warp * 512 + k * 32 + lane;
-        m[k] = __ballot_sync(0xffffffffu, t < T && valid[t]);
+        m[k] = __ballot_sync(0xffffffffu, t < T && mask_hit(valid[t], match));
         c += __popc(m[k]);
     }
     if (lane == 0) wcnt[warp] = c;
@@ -257,6 +260,40 @@ index_mask_kernel(const long long *__restrict__ idx, long long n, unsigned *__re
         if (atomicOr(mask_words + (t >> 2), bit) & bit) *dup = 1;
     }
 }
+// Row signatures of overlapping row sets: sig[t] has bit `bit` set when row t is listed in set `bit` (<= 62 sets).
+__global__ void __launch_bounds__(256)
+rows_or_bit_kernel(const long long *__restrict__ idx, long long n, unsigned long long bitmask,
+                   unsigned long long *__restrict__ sig, long long T) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const long long t = idx[i];
+        if (t >= 0 && t < T) atomicOr(sig + t, bitmask);
+    }
+}
+// Distinct signatures -> cells: a 256-slot open-addressing table (keys = signatures, ~0 = empty); cell_of[t] = slot of
+// row t's signature, counts[slot] = rows of the cell.  *overflow is set when more than 200 distinct signatures exist.
+__global__ void __launch_bounds__(256)
+cells_from_signatures_kernel(const unsigned long long *__restrict__ sig, long long T, unsigned char *__restrict__ cell_of,
+                             unsigned long long *__restrict__ keys, long long *__restrict__ counts, int *__restrict__ used,
+                             int *__restrict__ overflow) {
+    for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < T; t += (long long)gridDim.x * 256) {
+        const unsigned long long k = sig[t];
+        unsigned slot = (unsigned)((k * 0x9E3779B97F4A7C15ULL) >> 56);
+        int found = -1;
+        for (int probe = 0; probe < 256; ++probe, slot = (slot + 1) & 255u) {
+            unsigned long long cur = keys[slot];
+            if (cur == ~0ULL) {
+                if (atomicAdd(used, 0) >= 200) break;
+                cur = atomicCAS(keys + slot, ~0ULL, k);
+                if (cur == ~0ULL) { atomicAdd(used, 1); cur = k; }
+            }
+            if (cur == k) { found = (int)slot; break; }
+        }
+        if (found < 0) { *overflow = 1; cell_of[t] = 255; continue; }
+        cell_of[t] = (unsigned char)found;
+        atomicAdd((unsigned long long *)(counts + found), 1ULL);
+    }
+}
+
 // np.roll(y, shift): out[(i + shift) mod n] = y[i]   (backend/sglm_cv.py:95-96)
 __global__ void __launch_bounds__(256)
 roll_kernel(const double *__restrict__ y, long long n, long long shift, double *__restrict__ out) {
@@ -446,6 +483,34 @@ extern "C" int sglm_index_mask_u8(const int64_t *idx, int64_t n_idx, uint8_t *ma
     return SGLM_OK;
 }
 
+extern "C" int sglm_rows_or_bit_u64(const int64_t *idx, int64_t n_idx, int32_t bit, uint64_t *sig, int64_t T, void *stream) {
+    SGLM_CHECK_ARG(n_idx >= 0 && T >= 0 && bit >= 0 && bit < 63, SGLM_E_SHAPE, "rows_or_bit: bad argument");
+    if (n_idx == 0) return SGLM_OK;
+    SGLM_CHECK_ARG(idx && sig, SGLM_E_INVALID_ARG, "rows_or_bit: null pointer");
+    const int grid = (int)std::min<long long>(ceil_div<long long>(n_idx, 256), (long long)sm_count() * 16);
+    rows_or_bit_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const long long *)idx, n_idx, 1ULL << bit,
+                                                              (unsigned long long *)sig, T);
+    SGLM_LAUNCH_OK("rows_or_bit_kernel");
+    return SGLM_OK;
+}
+
+// table: 256 keys (uint64) then 256 counts (int64) then {used, overflow} (2 int32) = 4104 bytes, device memory
+extern "C" int sglm_cells_from_signatures(const uint64_t *sig, int64_t T, uint8_t *cell_of, void *table, void *stream) {
+    SGLM_CHECK_ARG(T >= 0, SGLM_E_SHAPE, "cells_from_signatures: bad shape");
+    SGLM_CHECK_ARG(sig && cell_of && table, SGLM_E_INVALID_ARG, "cells_from_signatures: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long *keys = (unsigned long long *)table;
+    long long *counts = (long long *)(keys + 256);
+    int *used = (int *)(counts + 256);
+    SGLM_CUDA_OK(cudaMemsetAsync(keys, 0xff, 256 * sizeof(unsigned long long), st));
+    SGLM_CUDA_OK(cudaMemsetAsync(counts, 0, 256 * sizeof(long long) + 2 * sizeof(int), st));
+    if (T == 0) return SGLM_OK;
+    const int grid = (int)std::min<long long>(ceil_div<long long>(T, 256), (long long)sm_count() * 16);
+    cells_from_signatures_kernel<<<grid, 256, 0, st>>>((const unsigned long long *)sig, T, cell_of, keys, counts, used, used + 1);
+    SGLM_LAUNCH_OK("cells_from_signatures_kernel");
+    return SGLM_OK;
+}
+
 extern "C" int sglm_roll_f64(const double *y, int64_t n, int64_t shift, double *out, void *stream) {
     SGLM_CHECK_ARG(n >= 0, SGLM_E_SHAPE, "roll: negative size");
     if (n == 0) return SGLM_OK;
@@ -462,8 +527,23 @@ extern "C" size_t sglm_mask_compact_workspace_bytes(int64_t T) {
     return (size_t)std::max<long long>(1, ceil_div<long long>(T, CMP_CH)) * sizeof(long long);
 }
 
+static int mask_compact(const uint8_t *valid, int64_t T, int match, int64_t *rows, void *workspace,
+                        size_t workspace_bytes, void *stream);
+
 extern "C" int sglm_mask_compact_rows(const uint8_t *valid, int64_t T, int64_t *rows, void *workspace,
                                       size_t workspace_bytes, void *stream) {
+    return mask_compact(valid, T, -1, rows, workspace, workspace_bytes, stream);
+}
+
+// rows whose byte equals `match` (the cell ids written by sglm_cells_from_signatures), ascending
+extern "C" int sglm_match_compact_rows(const uint8_t *ids, int64_t T, int32_t match, int64_t *rows, void *workspace,
+                                       size_t workspace_bytes, void *stream) {
+    SGLM_CHECK_ARG(match >= 0 && match < 256, SGLM_E_INVALID_ARG, "match_compact: match must be a byte value");
+    return mask_compact(ids, T, match, rows, workspace, workspace_bytes, stream);
+}
+
+static int mask_compact(const uint8_t *valid, int64_t T, int match, int64_t *rows, void *workspace,
+                        size_t workspace_bytes, void *stream) {
     SGLM_CHECK_ARG(T >= 0, SGLM_E_SHAPE, "mask_compact: bad shape");
     if (T == 0) return SGLM_OK;
     SGLM_CHECK_ARG(valid && rows && workspace, SGLM_E_INVALID_ARG, "mask_compact: null pointer");
@@ -472,11 +552,11 @@ extern "C" int sglm_mask_compact_rows(const uint8_t *valid, int64_t T, int64_t *
     SGLM_CHECK_ARG(nb <= 0x7fffffffLL, SGLM_E_SHAPE, "mask_compact: too many rows");
     cudaStream_t st = (cudaStream_t)stream;
     long long *offs = (long long *)workspace;
-    mask_block_count_kernel<<<(unsigned)nb, 256, 0, st>>>(valid, T, offs);
+    mask_block_count_kernel<<<(unsigned)nb, 256, 0, st>>>(valid, T, match, offs);
     SGLM_LAUNCH_OK("mask_block_count_kernel");
     exclusive_scan_kernel<<<1, 1024, 0, st>>>(offs, nb);
     SGLM_LAUNCH_OK("exclusive_scan_kernel");
-    mask_compact_kernel<<<(unsigned)nb, 256, 0, st>>>(valid, T, offs, (long long *)rows);
+    mask_compact_kernel<<<(unsigned)nb, 256, 0, st>>>(valid, T, match, offs, (long long *)rows);
     SGLM_LAUNCH_OK("mask_compact_kernel");
     return SGLM_OK;
 }
