@@ -534,7 +534,7 @@ def _CD_DEFAULT_PLAN(C, n_models):
     # (config 1: CD 5.6 -> 4.3 ms).  Narrow designs keep one CTA per model.
     if C > 1024 and n_models >= 16:
         heavy = 0.3 * n_models
-        for m, k, sm_budget in ((2, 4, 160), (4, 4, 240)):
+        for m, k, sm_budget in ((2, 4, 240), (4, 4, 240)):
             if -(-heavy // m) * k <= sm_budget:
                 return f"{m}x{k}@0.3,0x0"
         return "4x2@0.3,0x0"
