@@ -1131,6 +1131,9 @@ def _poisson_batch(Xd, Yd, models, RW):
     keep = {}
     wb_of = {}
 
+    refreshed_at = {g: 0 for g in range(n_h)}
+    n_refresh = {g: 1 for g in range(n_h)}
+
     def refresh(g, ref):
         """New H~ of group g from the current iterate of model `ref`, new factors for the group's models."""
         rw, fi = gkeys[g]
@@ -1153,20 +1156,45 @@ def _poisson_batch(Xd, Yd, models, RW):
         sel = _dev(idxs, np.int64)
         last_step[sel] = 0.0                      # the contraction estimate restarts with the new Hessian
         ratio_out[sel] = 1.0
+        if g in borrowed:                         # the group now has its own Hessian
+            hess_id[sel] = hess_true[sel]
+            hscale[sel] = 1.0
+            del borrowed[g]
 
+    # First step: every model starts from w = 0, b = log(mean y), where the Hessian is mean(y) * X'X over the model's
+    # rows.  A fold whose parameter sets also have a full-data model (the refit of every CV set) borrows that group's
+    # Hessian and factors for this one step, scaled by its share of sum(y) — 1 weighted Gram and 1 factorisation per
+    # alpha instead of one per (fold, alpha); its own Hessian follows with the refresh after the first step.
+    hscale = torch.ones(B, dtype=torch.float64, device="cuda")
+    borrowed = {}
+    for g, (rw, fi) in enumerate(gkeys):
+        if rw < 0 or (-1, fi) not in groups:
+            continue
+        g0 = gkeys.index((-1, fi))
+        by_alpha = {(models[i].alpha, models[i].ycol == 0): i for i in groups[gkeys[g0]]}
+        pairs = [(i, by_alpha.get((models[i].alpha, True))) for i in groups[gkeys[g]]]
+        if all(j is not None for _, j in pairs):
+            borrowed[g] = (g0, pairs)
     for g in range(n_h):
-        refresh(g, groups[gkeys[g]][0])
+        if g not in borrowed:
+            refresh(g, groups[gkeys[g]][0])
+    hess_true = hess_id.clone()
+    for g, (g0, pairs) in borrowed.items():
+        mine = _dev([i for i, _ in pairs], np.int64)
+        theirs = _dev([j for _, j in pairs], np.int64)
+        hess_id[mine] = g0
+        L_of[mine] = L_of[theirs]
+        share = np.array([info[(models[i].rw, models[i].ycol)][1] / info[(models[j].rw, models[j].ycol)][1] for i, j in pairs])
+        hscale[mine] = _dev(share, f64)
     n_words = nat.lib().sglm_pb_state_words()
     fields = [W, Wprev, Wnew, rhs, b, bprev, fprev, fcur, last_step, step_out, ratio_out, halv, n_iter, status, flag,
-              has_prev, alpha, n_tot_d, tol, fit_icpt, max_iter, hess_id, HQ, Hxbar, Hh11, sums, Gw]
+              has_prev, alpha, n_tot_d, tol, fit_icpt, max_iter, hess_id, HQ, Hxbar, Hh11, sums, Gw, hscale]
     words = [t.data_ptr() for t in fields] + [ldw, ldq, ldb, C | (B << 32)]
     if len(words) != n_words:
         raise nat.SglmNativeError(f"poisson batch: state layout mismatch ({len(words)} words, library expects {n_words})")
     state = np.array(words, dtype=np.uint64)
     state_p = state.ctypes.data_as(ctypes.c_void_p)
     RWp, ldrw = (ptr(RW), RW.stride(0)) if RW is not None else (None, 0)
-    refreshed_at = {g: 0 for g in range(n_h)}
-    n_refresh = {g: 1 for g in range(n_h)}
     it = 0
     max_rounds = int(max(m.max_iter for m in models)) + 40
     while it < max_rounds:

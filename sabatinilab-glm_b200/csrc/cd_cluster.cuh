@@ -533,7 +533,7 @@ enet_cd_cluster_kernel(const double *const *__restrict__ prob_Q, const double *c
                     auto candidate = [&]() -> double {
                         const double rr = r_l;
                         const double dpos = fma(rr, inv_l, k_pos), dneg = fma(rr, inv_l, k_neg);
-                        return (rr > l1) ? dpos : ((rr < -l1) ? dneg : negw);
+                        return cd_soft_select(rr, l1, dpos, dneg, negw);
                     };
                     if (pmv[m * NBLK + b] >= 20) {
                         // dense block (20+ coordinates moved in the last sweep): straight-line, a screened-out

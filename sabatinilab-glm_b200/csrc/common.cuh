@@ -44,6 +44,21 @@ inline int sm_count() {
 template <typename T>
 __host__ __device__ inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
 
+// Soft-threshold branch select of the coordinate-descent step, (r > l1) ? dpos : ((r < -l1) ? dneg : other), as two
+// predicated selects.  Written in PTX because the compiler otherwise turns the nested conditional into a divergent
+// branch around the second FMA (BSSY / BRA / BSYNC + a BRA.DIV convergence check before the next shuffle) — on the
+// 32-step dependent chain that bounds the heaviest models (ncu source view, profiles/r2_cd_experiments.txt §5).
+__device__ __forceinline__ double cd_soft_select(double r, double l1, double dpos, double dneg, double other) {
+    double out;
+    asm("{\n\t.reg .pred p, q;\n\t"
+        "setp.gt.f64 p, %1, %2;\n\t"
+        "setp.lt.f64 q, %1, %3;\n\t"
+        "selp.f64 %0, %5, %6, q;\n\t"
+        "selp.f64 %0, %4, %0, p;\n\t}"
+        : "=&d"(out) : "d"(r), "d"(l1), "d"(-l1), "d"(dpos), "d"(dneg), "d"(other));
+    return out;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

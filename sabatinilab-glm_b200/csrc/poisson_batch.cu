@@ -269,6 +269,8 @@ struct PbState {
     const double *Hh11;                      // [n_hess] sum of the weights
     const double *sums;                      // [B][4] from the epilogue
     const double *Gw;                        // [C][ldb] gradient X'R
+    const double *hscale;                    // [B] the model's Hessian = hscale * (the group's H~): a fold's first step
+                                             // borrows the full-data Hessian scaled by its share of sum(y)
     long long ldw, ldq, ldb;
     int C, B;
 };
@@ -318,14 +320,17 @@ pb_rhs_kernel(PbState s) {
     const double *xbar = s.Hxbar[h];
     const double g_b = s.sums[4 * m + 3];
     const bool icpt = s.fit_icpt[m] != 0;
+    const double inv_hs = 1.0 / s.hscale[m];
     double *rhs = s.rhs + (long long)m * s.ldw;
     const int warp = tid >> 5, lane = tid & 31;
+    // (hs Q + a n I) w_new = hs Q w - g + xbar g_b   <=>   (Q + (a n / hs) I) w_new = Q w + (-g + xbar g_b) / hs ; the cached
+    // factor belongs to Q + a n' I with a n' ~ a n / hs (exact for hs = 1)
     for (int j = warp; j < s.C; j += 8) {
         const double *row = Q + (long long)j * s.ldq;
         double d = 0.0;
         for (int k = lane; k < s.C; k += 32) d = fma(row[k], wsh[k], d);
         d = warp_sum(d);
-        if (lane == 0) rhs[j] = d - s.Gw[(long long)j * s.ldb + m] + (icpt ? xbar[j] * g_b : 0.0);
+        if (lane == 0) rhs[j] = d + (-s.Gw[(long long)j * s.ldb + m] + (icpt ? xbar[j] * g_b : 0.0)) * inv_hs;
     }
     if (tid == 0) { s.halv[m] = 0; s.fcur[m] = f; s.flag[m] = 1; }
 }
@@ -352,7 +357,7 @@ pb_finish_kernel(PbState s) {
     dw = pb_block_max(dw, sh);
     wmax = pb_block_max(wmax, sh);
     const double b_old = s.b[m];
-    const double b_new = icpt ? b_old - s.sums[4 * m + 3] / s.Hh11[h] - dot : 0.0;
+    const double b_new = icpt ? b_old - s.sums[4 * m + 3] / (s.Hh11[h] * s.hscale[m]) - dot : 0.0;
     for (int j = tid; j < s.C; j += 256) { wp[j] = w[j]; w[j] = wn[j]; }
     if (tid == 0) {
         const double step = fmax(dw, fabs(b_new - b_old)) / fmax(1.0, wmax);

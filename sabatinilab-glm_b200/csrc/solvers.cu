@@ -322,7 +322,7 @@ enet_cd_gram_kernel(const double *const *__restrict__ prob_Q, const double *cons
                 auto candidate = [&]() -> double {
                     const double r = r_l;
                     const double dpos = fma(r, inv_l, k_pos), dneg = fma(r, inv_l, k_neg);
-                    const double dc = (r > l1) ? dpos : ((r < -l1) ? dneg : -w_l);
+                    const double dc = cd_soft_select(r, l1, dpos, dneg, -w_l);
                     return ok_l ? dc : 0.0;
                 };
                 if (pmv[b] >= 20) {
