@@ -483,6 +483,8 @@ def _cd_shape_ok(g, k, C):
         return 0, 0
     while k > 1 and (C + 31) // 32 < 2 * k:
         k //= 2
+    if g == 8 and k < 2:
+        g = 4                 # groups of 8 exist for clusters of 2+ CTAs only
     if not nat.lib().sglm_enet_cd_cluster_supported(g, k):
         raise nat.SglmNativeError(f"coordinate descent: unsupported (group, cluster) = ({g}, {k})")
     # very wide designs: a CTA's column slice (w and Qw of every model of the group) must fit in shared memory
@@ -498,11 +500,11 @@ def _cd_shape_ok(g, k, C):
     return g, k
 
 
-def _cd_plan(C, n_models):
+def _cd_plan(C, n_models, n_probs=1):
     """Parts of the coordinate-descent launch: [(first slot, end slot, group size M, cluster size K)] over
-    the cost-ordered model list (heaviest first).  Plan text: comma-separated `MxK[@fraction]`; a part
-    takes `fraction` of the models (the last part takes the rest); `0x0` is the first-generation
-    one-CTA-per-model kernel.  CD_GROUP / CD_CLUSTER (or SGLM_CD_GROUP / SGLM_CD_CLUSTER) give a
+    the cost-ordered model list (heaviest first).  Plan text: comma-separated `MxK[@fraction]` or `MxK[#count]`;
+    a part takes `fraction` of the models / `count` models (the last part takes the rest); `0x0` is the
+    first-generation one-CTA-per-model kernel.  CD_GROUP / CD_CLUSTER (or SGLM_CD_GROUP / SGLM_CD_CLUSTER) give a
     one-part plan."""
     import os
     g = CD_GROUP if CD_GROUP is not None else os.environ.get("SGLM_CD_GROUP")
@@ -511,25 +513,38 @@ def _cd_plan(C, n_models):
     if g is not None or k is not None:
         text = f"{int(1 if g is None else g)}x{int(1 if k is None else k)}"
     if text is None:
-        text = _CD_DEFAULT_PLAN(C, n_models)
+        text = _CD_DEFAULT_PLAN(C, n_models, n_probs)
     parts, r0 = [], 0
     items = [t for t in text.split(",") if t]
     for n, item in enumerate(items):
-        shape, _, frac = item.partition("@")
+        shape, sep, frac = item.partition("@")
+        if not sep:
+            shape, sep, count = item.partition("#")
+            frac = ""
+        else:
+            count = ""
         gg, kk = (int(v) for v in shape.split("x"))
-        r1 = n_models if (n == len(items) - 1 or not frac) else min(n_models, r0 + int(round(float(frac) * n_models)))
+        if n == len(items) - 1 or not (frac or count):
+            r1 = n_models
+        elif count:
+            r1 = min(n_models, r0 + int(count))
+        else:
+            r1 = min(n_models, r0 + int(round(float(frac) * n_models)))
         gg, kk = _cd_shape_ok(gg, kk, C)
         parts.append((r0, r1, gg, kk))
         r0 = r1
     return parts
 
 
-def _CD_DEFAULT_PLAN(C, n_models):
+def _CD_DEFAULT_PLAN(C, n_models, n_probs=1):
     # wide designs: the heaviest 30 % of the cost-ordered grid as groups of M models of one fold on K-CTA clusters,
     # the light rest concurrently on the one-CTA-per-model kernel.  A model is a serial chain of 32-coordinate
-    # blocks; measured per block for the heaviest model (profiles/r2_cd_experiments.txt): 6.1 us on (4,2), 4.75 us
-    # on (4,4), 4.15 us on (2,4) — wider clusters shorten the chain but need more SMs per model, so the shape follows
-    # the number of models this GPU holds (a whole grid: (4,2); a share of a grid dealt over several GPUs: wider).
+    # blocks; measured per block for the heaviest model (profiles/r2_cd_experiments.txt): 6.1 us on (4,2), 4.0 us
+    # on (4,4), 3.4 us on (2,4) — wider clusters shorten the chain but need more SMs per model, so the shape follows
+    # the number of models this GPU holds: a share of a grid dealt over several GPUs gets the wide shapes throughout;
+    # a whole grid puts only its chain-critical head (the heaviest group of every problem: 4 models x n_probs) on
+    # (4,4) and the rest of the heavy part on (4,2) — the launch is then bound by SM time, not by the longest chain
+    # (1500 models: 354 -> 288 ms, experiments log section 7).
     # A handful of models (a single GLM.fit) leaves the GPU idle anyway: each model gets a 4-CTA cluster
     # (config 1: CD 5.6 -> 4.3 ms).  Narrow designs keep one CTA per model.
     if C > 1024 and n_models >= 16:
@@ -537,6 +552,9 @@ def _CD_DEFAULT_PLAN(C, n_models):
         for m, k, sm_budget in ((2, 4, 240), (4, 4, 240)):
             if -(-heavy // m) * k <= sm_budget:
                 return f"{m}x{k}@0.3,0x0"
+        head = 4 * max(1, n_probs)
+        if head <= 0.1 * n_models:
+            return f"4x4#{head},4x2#{int(round(heavy)) - head},0x0"
         return "4x2@0.3,0x0"
     if C >= 256 and n_models <= 8:
         return "1x4"
@@ -619,7 +637,7 @@ def solve_models(models, C, do_screening=True):
             # launch plan: consecutive parts of the cost-ordered model list, each with its own kernel shape
             # (models per cluster x CTAs per cluster; 0x0 = first-generation kernel), each on its own
             # stream so that clusters of heavy models and dense packs of light models share the SMs
-            parts = _cd_plan(C, n_slots)
+            parts = _cd_plan(C, n_slots, len(probs))
             tm_d = None
             if any(g for _, _, g, _ in parts):
                 qh = np.array([p.Qc.data_ptr() for p in probs], dtype=np.uint64)
@@ -667,7 +685,8 @@ def solve_models(models, C, do_screening=True):
                             cd_parts_log.append(dict(shape=(0, 0), slots=(r0, r1), group_stats=None, info=info_d))
                         call("sglm_enet_cd_gram_f64", ptr(Qp), ptr(qp), ptr(dp), ptr(yy), ldq, C, ptr(pack_i[0][r0:]),
                              ptr(pack_f[0][r0:]), ptr(pack_f[1][r0:]), ptr(pack_f[2][r0:]), ptr(pack_i[1][r0:]),
-                             r1 - r0, int(warm), int(do_screening), ptr(Wcd[r0:]), ldw, ptr(info_d[r0:]), stream_ptr())
+                             r1 - r0, int(warm) | (int(CD_DEBUG_TIMER) << 8), int(do_screening), ptr(Wcd[r0:]), ldw,
+                             ptr(info_d[r0:]), stream_ptr())
                     if st is not main:
                         ev = torch.cuda.Event()
                         ev.record(st)

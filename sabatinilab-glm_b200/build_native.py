@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["timeshift.cu", "suffstats.cu", "gram_tc.cu", "solvers.cu", "cd_cluster.cu", "cd_cluster_m1.cu", "cd_cluster_m2.cu", "cd_cluster_m4.cu", "predict.cu", "microbench.cu", "minnorm.cu", "poisson_batch.cu", "preprocess.cu"]
+SOURCES = ["timeshift.cu", "suffstats.cu", "gram_tc.cu", "solvers.cu", "cd_cluster.cu", "cd_cluster_m1.cu", "cd_cluster_m2.cu", "cd_cluster_m4.cu", "cd_cluster_m8.cu", "predict.cu", "microbench.cu", "minnorm.cu", "poisson_batch.cu", "preprocess.cu"]
 LIB = os.path.join(HERE, "libsglm_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-cudart", "static"]

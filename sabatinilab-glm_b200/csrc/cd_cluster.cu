@@ -1,5 +1,5 @@
 // C-ABI entry of the cluster coordinate-descent kernel (kernel: cd_cluster.cuh; instantiations per
-// group size: cd_cluster_m{1,2,4}.cu).
+// group size: cd_cluster_m{1,2,4,8}.cu).
 #include <stdlib.h>
 
 #include "cd_cluster.cuh"
@@ -8,6 +8,7 @@ using namespace sglm;
 
 extern "C" int sglm_enet_cd_cluster_supported(int32_t group_size, int32_t cluster_size) {
     const int M = group_size, K = cluster_size;
+    if (M == 8) return (K == 2 || K == 4 || K == 8) ? 1 : 0;
     return ((M == 1 || M == 2 || M == 4) && (K == 1 || K == 2 || K == 4 || K == 8)) ? 1 : 0;
 }
 
@@ -83,5 +84,6 @@ extern "C" int sglm_enet_cd_cluster_f64(const double *const *prob_Q, const doubl
     if (const char *v = getenv("SGLM_CDC_VARIANT")) a.variant = atoi(v);      // tuning switch
     if (group_size == 1) return cdc::launch_m1(a, cluster_size);
     if (group_size == 2) return cdc::launch_m2(a, cluster_size);
+    if (group_size == 8) return cdc::launch_m8(a, cluster_size);
     return cdc::launch_m4(a, cluster_size);
 }

@@ -282,6 +282,7 @@ enet_cd_cluster_kernel(const double *const *__restrict__ prob_Q, const double *c
     const int dbg_sel = warm_start >> 8;      // diagnostics: which timer info[6m+5] reports
     warm_start &= 1;
     const long long t_begin = clock64();
+    const unsigned long long gt_begin = global_timer_ns();
     unsigned rc = 0u;             // records published so far (identical in every thread of the cluster)
     long long rows_loaded = 0;    // panel warps: rows of Q the records asked for (union over the M models)
     unsigned xpar = 0u;
@@ -663,6 +664,36 @@ enet_cd_cluster_kernel(const double *const *__restrict__ prob_Q, const double *c
                                 acc[mm][u] = okc[u] ? Qw2[mm * CoP2 + c0 + u * NTB] : make_double2(0.0, 0.0);
                         }
                         unsigned rem = um;
+                        if constexpr (M >= 8) {
+                            // wide groups: the deltas stay in shared memory until the row they scale has arrived
+                            // (M * RG of them in registers next to M * CH accumulators would not fit)
+                            while (rem) {
+                                double2 v[RG][CH];
+                                int ii[RG];
+#pragma unroll
+                                for (int g = 0; g < RG; ++g) {
+                                    const bool has = rem != 0u;
+                                    const int i = has ? (__ffs(rem) - 1) : 32;
+                                    rem &= rem - 1;
+                                    ii[g] = i;
+                                    const double2 *row = Q2 + (long long)(i & 31) * ld2 + c0;
+#pragma unroll
+                                    for (int u = 0; u < CH; ++u)
+                                        v[g][u] = okc[u] ? __ldg(row + u * NTB) : make_double2(0.0, 0.0);
+                                }
+#pragma unroll
+                                for (int g = 0; g < RG; ++g)
+#pragma unroll
+                                    for (int mm = 0; mm < M; ++mm) {
+                                        const double dd = dlm[mm][ii[g]];
+#pragma unroll
+                                        for (int u = 0; u < CH; ++u) {
+                                            acc[mm][u].x = fma(dd, v[g][u].x, acc[mm][u].x);
+                                            acc[mm][u].y = fma(dd, v[g][u].y, acc[mm][u].y);
+                                        }
+                                    }
+                            }
+                        } else {
                         while (rem) {
                             double2 v[RG][CH];
                             double d[RG][M];
@@ -687,6 +718,7 @@ enet_cd_cluster_kernel(const double *const *__restrict__ prob_Q, const double *c
                                         acc[mm][u].x = fma(d[g][mm], v[g][u].x, acc[mm][u].x);
                                         acc[mm][u].y = fma(d[g][mm], v[g][u].y, acc[mm][u].y);
                                     }
+                        }
                         }
 #pragma unroll
                         for (int u = 0; u < CH; ++u)
@@ -731,7 +763,8 @@ enet_cd_cluster_kernel(const double *const *__restrict__ prob_Q, const double *c
         info[6 * mdl + 2] = par[m * 8 + 7];
         info[6 * mdl + 3] = su;
         info[6 * mdl + 4] = sb;
-        info[6 * mdl + 5] = st / (double)max(1LL, clock64() - t_begin);
+        info[6 * mdl + 5] = dbg_sel == 6 ? (double)gt_begin : dbg_sel == 7 ? (double)(global_timer_ns() - gt_begin)
+                                         : st / (double)max(1LL, clock64() - t_begin);
     }
 }
 
@@ -816,9 +849,22 @@ static int launch_group(const Args &a, int K) {
     return fail(SGLM_E_UNSUPPORTED, "enet_cd_cluster: unsupported cluster size %d", K);
 }
 
+// Groups of 8 models: 8 register warps + 8 panel warps (512 threads, 128 registers each), one 16-byte column
+// chunk per panel thread and pass (the chunk loop covers wider slices), 8 row loads in flight per thread.
+template <int M>
+static int launch_group_wide(const Args &a, int K) {
+    switch (K) {
+        case 2: return launch_a<M, 2, 8, 1, 8, 1>(a);
+        case 4: return launch_a<M, 4, 8, 1, 8, 1>(a);
+        case 8: return launch_a<M, 8, 4, 1, 8, 1>(a);
+    }
+    return fail(SGLM_E_UNSUPPORTED, "enet_cd_cluster: unsupported cluster size %d for groups of %d", K, M);
+}
+
 int launch_m1(const Args &a, int K);
 int launch_m2(const Args &a, int K);
 int launch_m4(const Args &a, int K);
+int launch_m8(const Args &a, int K);
 
 }  // namespace cdc
 }  // namespace sglm

@@ -155,6 +155,9 @@ enet_cd_gram_kernel(const double *const *__restrict__ prob_Q, const double *cons
     const int Cp2 = Cp >> 1;
     const bool is_seq = warp == 0;
     const bool screening = do_screening && (l1 != 0.0);
+    const int dbg_sel = warm_start >> 8;      // diagnostics: what info[6m+5] reports (6: start time, 7: duration, ns)
+    warm_start &= 1;
+    const unsigned long long gt_begin = global_timer_ns();
 
     for (int i = tid; i < Cp; i += NT) { w[i] = (warm_start && i < C) ? W[(long long)mdl * ldw + i] : 0.0; Qw[i] = 0.0; }
     if (tid == 0) { ctl[0] = 0u; ctl[1] = 0u; }
@@ -450,7 +453,8 @@ enet_cd_gram_kernel(const double *const *__restrict__ prob_Q, const double *cons
             info[6 * mdl + 2] = (double)n_iter;
             info[6 * mdl + 3] = (double)n_upd;
             info[6 * mdl + 4] = (double)n_blk;
-            info[6 * mdl + 5] = (double)t_p1 / (double)max(1LL, clock64() - t_begin);   // share of time in the register phase
+            info[6 * mdl + 5] = dbg_sel == 6 ? (double)gt_begin : dbg_sel == 7 ? (double)(global_timer_ns() - gt_begin)
+                              : (double)t_p1 / (double)max(1LL, clock64() - t_begin);   // share of time in the register phase
         }
     }
 }

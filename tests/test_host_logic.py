@@ -167,7 +167,13 @@ def test_cd_launch_plan_parsing():
         assert eng._cd_plan(410, 1500) == [(0, 1500, 0, 0)]       # narrow design: one CTA per model
         assert eng._cd_plan(410, 1) == [(0, 1, 1, 4)]             # a single fit: one 4-CTA cluster
         assert eng._cd_plan(100, 1) == [(0, 1, 0, 0)]
-        assert eng._cd_plan(2000, 1500)[0][2:] == (4, 2)
+        assert eng._cd_plan(2000, 1500)[0][2:] == (4, 4)
+        # a whole grid: the heaviest group of every problem on (4,4), the rest of the heavy 30 % on (4,2)
+        assert eng._cd_plan(2000, 1500, 6) == [(0, 24, 4, 4), (24, 450, 4, 2), (450, 1500, 0, 0)]
+        assert eng._cd_plan(2000, 188, 6) == [(0, 56, 2, 4), (56, 188, 0, 0)]      # an eighth of a grid: wide clusters
+        eng.CD_PLAN = "4x4#24,4x2#100,0x0"
+        assert eng._cd_plan(2000, 1500) == [(0, 24, 4, 4), (24, 124, 4, 2), (124, 1500, 0, 0)]
+        eng.CD_PLAN = None
         eng.CD_PLAN = "4x2"
         assert eng._cd_plan(6000, 100) == [(0, 100, 4, 4)]       # slice of 3000 columns x 4 models does not fit: wider cluster
         assert eng._cd_plan(20000, 100)[0][2] in (1, 2)          # ... then smaller groups
