@@ -210,6 +210,40 @@ int sglm_gram_tc_cells_combine_f64(int32_t C, int32_t n_y, const int32_t *colE, 
                                    int32_t n_out, double *G, int64_t ldg, void *workspace, size_t workspace_bytes,
                                    void *stream);
 
+/* Lag designs WITHOUT the design matrix.  A column of a lag design (backend/sglm_pp.py:23-103 timeshift /
+ * timeshift_multiple) is a base signal read at another row: Z[t, c] = base[t + off[c], src[c]].  Its digit planes are
+ * the base signal's planes read at another position, so the statistics need neither the T x (P*L) fp64 design nor a
+ * pass over it: the P base signals are sliced once, the K-major int8 operand is a byte gather from those planes
+ * (tc_expand_kernel), the GEMM / cell sums / recombination are the ordinary ones.
+ *   base       : device, the window of the base signals every column reads (n_u rows, row stride ldb);
+ *   src / off  : host [C]; design row t of column c = window row t + off[c] (0 <= off[c], off[c] + T <= n_u);
+ *   baseE / baseS (device) and baseS_host : scale exponents and digit planes of [base | 1] (P + 1 entries) over the
+ *                window (sglm_gram_tc_colstats_f64 + sglm_gram_tc_exponents on the window); the caller gives every
+ *                lag column the exponent and plane count of its base signal: colE[c] = baseE[src[c]], colS likewise;
+ *                the entries of the response columns and the ones column (c >= C) come from the same two calls on Y.
+ *   n_out == 0 : the row lists are the sets; n_out > 0: cells + membership (sglm_gram_tc_cells_f64);
+ *   partial    : stop after the int64 plane Grams of the sets (row-sharded use), finish with
+ *                sglm_gram_tc_cells_combine_f64 on the same workspace. */
+typedef struct sglm_lag_design {
+    const double *base;
+    int64_t ldb;
+    int64_t n_u;
+    int32_t P;
+    const int32_t *src_host;
+    const int32_t *off_host;
+    const int32_t *baseE;
+    const int32_t *baseS;
+    const int32_t *baseS_host;
+} sglm_lag_design;
+size_t sglm_gram_tc_lag_workspace_bytes(int32_t n_aug, const int32_t *colS_host, int32_t n_cells,
+                                        const int64_t *cell_rows_host, int32_t n_out, int32_t P,
+                                        const int32_t *baseS_host, int64_t n_u);
+int sglm_gram_tc_lag_cells_f64(const sglm_lag_design *lag, const double *Y, int64_t ldy, int32_t n_y, int64_t T,
+                               int32_t C, const int32_t *colE, const int32_t *colS, const int32_t *colS_host,
+                               int32_t n_cells, const int64_t *cell_rows_host, const int64_t *rows, int32_t n_out,
+                               const int32_t *member_host, double *G, int64_t ldg, void *workspace,
+                               size_t workspace_bytes, int32_t partial, void *stream);
+
 /* Index lists -> per-row multiplicities: counts[idx[i]] += 1 (the fold row sets of
  * backend/sglm_cv.py:106-110, X[idx_train,:] / X[idx_test,:]).  counts must be zeroed. */
 int sglm_index_counts_f64(const int64_t *idx, int64_t n_idx, double *counts, int64_t T,

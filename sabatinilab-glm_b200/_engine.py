@@ -131,6 +131,81 @@ def gather(Xd, col_src, col_shift, fill_value):
     return out
 
 
+class LagRecipe:
+    """A lag design that has not been built: base signals on the device + column map + a contiguous row range
+    (what `sglm_pp.DeviceDesign` holds after `dropna()`).  Design row t (0-based inside the range), column c is
+    base[lo + t - sh[c], src[c]].  The tensor-core statistics are computed from the base signals alone
+    (suffstats_tc -> sglm_gram_tc_lag_cells_f64: the 32 GB design of BASELINE configs[2] is neither written nor read);
+    everything else asks for `tensor()`, which gathers the design once (cached)."""
+
+    def __init__(self, base, src, sh, lo, hi, fill, cache=None):
+        self.base = base
+        self.src = np.ascontiguousarray(src, dtype=np.int32)
+        self.sh = np.ascontiguousarray(sh, dtype=np.int32)
+        self.lo, self.hi, self.fill = int(lo), int(hi), fill
+        self._cache = cache
+
+    @property
+    def shape(self):
+        return (max(self.hi - self.lo, 0), int(self.src.shape[0]))
+
+    def window(self):
+        """(u0, n_u, off): rows [u0, u0 + n_u) of the base signals hold everything the design reads, design row t of
+        column c is window row t + off[c]; None when a column reads outside the base signals (fill values)."""
+        if self.src.shape[0] == 0 or self.hi <= self.lo:
+            return None
+        u0, u1 = self.lo - int(self.sh.max()), self.hi - int(self.sh.min())
+        if u0 < 0 or u1 > int(self.base.shape[0]):
+            return None
+        return u0, u1 - u0, np.ascontiguousarray(self.lo - self.sh - u0, dtype=np.int32)
+
+    def tensor(self):
+        if self._cache is None:
+            self._cache = gather(self.base, self.src, self.sh, self.fill)[self.lo:self.hi]
+        return self._cache
+
+
+def device_design(X):
+    """device_matrix(X), except that a device-resident lag design with a contiguous row range stays a recipe
+    (LagRecipe) — the Gaussian CV grid computes its statistics from the base signals."""
+    if type(X).__name__ == "DeviceDesign":
+        r = X.lag_recipe()
+        if r is not None:
+            return r
+    return device_matrix(X)
+
+
+def _lag_analysis(Xr, Yd, win, all_reduce=None):
+    """Column analysis of a lag design from its base signals: exponents / digit planes of [base | 1] over the window
+    (every lag column inherits those of its base signal) and of [Y | 1].  Returns device colE, colS [n_aug],
+    baseE, baseS [P + 1] and a device flag tensor (NaN / inf seen)."""
+    torch = nat.require_cuda()
+    u0, n_u, _ = win
+    P = int(Xr.base.shape[1])
+    n_y = Yd.shape[1]
+    T = Xr.shape[0]
+    bw = Xr.base[u0:u0 + n_u]
+    cm_b = torch.empty(P + 1, dtype=torch.int64, device="cuda")
+    ls_b = torch.empty(P + 1, dtype=torch.int32, device="cuda")
+    cm_y = torch.empty(n_y + 1, dtype=torch.int64, device="cuda")
+    ls_y = torch.empty(n_y + 1, dtype=torch.int32, device="cuda")
+    call("sglm_gram_tc_colstats_f64", ptr(bw), row_stride(bw), None, 0, 0, n_u, P, ptr(cm_b), ptr(ls_b), stream_ptr())
+    call("sglm_gram_tc_colstats_f64", None, 0, ptr(Yd), row_stride(Yd), n_y, T, 0, ptr(cm_y), ptr(ls_y), stream_ptr())
+    if all_reduce is not None:
+        cm = torch.cat([cm_b, cm_y]); ls = torch.cat([ls_b, ls_y])
+        all_reduce(cm, "max"); all_reduce(ls, "min")
+        cm_b, cm_y, ls_b, ls_y = cm[:P + 1].contiguous(), cm[P + 1:].contiguous(), ls[:P + 1].contiguous(), ls[P + 1:].contiguous()
+    bE = torch.empty(P + 1, dtype=torch.int32, device="cuda")
+    yE = torch.empty(n_y + 1, dtype=torch.int32, device="cuda")
+    flags = torch.empty(2, dtype=torch.int32, device="cuda")
+    call("sglm_gram_tc_exponents", ptr(cm_b), P + 1, 8, ptr(bE), ptr(ls_b), ptr(flags[0:]), stream_ptr())
+    call("sglm_gram_tc_exponents", ptr(cm_y), n_y + 1, 8, ptr(yE), ptr(ls_y), ptr(flags[1:]), stream_ptr())
+    src_t = _dev(Xr.src, np.int64)
+    colE = torch.cat([bE.index_select(0, src_t), yE]).contiguous()
+    colS = torch.cat([ls_b.index_select(0, src_t), ls_y]).contiguous()
+    return colE, colS, bE, ls_b, flags
+
+
 # --------------------------------------------------------------------------- #
 # sufficient statistics
 # --------------------------------------------------------------------------- #
@@ -210,21 +285,36 @@ def suffstats_tc(Xd, Yd, set_rows, check_gemm=False):
     set_rows: list with one entry per set — None (all rows) or a sorted, duplicate-free int64
     CUDA tensor of row indices.  Returns G [n_sets, n_aug, ldg]."""
     torch = nat.require_cuda()
+    lag = win = None
+    if isinstance(Xd, LagRecipe):
+        win = None if check_gemm else Xd.window()
+        if win is None:
+            Xd = Xd.tensor()
+        else:
+            lag = Xd
     T, C = Xd.shape
     n_y = Yd.shape[1]
     n_aug = C + n_y + 1
     n_sets = len(set_rows)
     ldg = _round_up(n_aug, 8)
-    colE = torch.empty(n_aug, dtype=torch.int32, device="cuda")
-    colS = torch.empty(n_aug, dtype=torch.int32, device="cuda")
-    scratch = torch.empty(n_aug, dtype=torch.int64, device="cuda")
-    flag = torch.empty(1, dtype=torch.int32, device="cuda")
-    call("sglm_gram_tc_analyze_f64", ptr(Xd), row_stride(Xd), ptr(Yd), row_stride(Yd), n_y, T, C, ptr(colE),
-         ptr(colS), ptr(scratch), ptr(flag), stream_ptr())
-    host = torch.cat([colS, flag]).cpu().numpy()
-    if host[-1] != 0:
-        raise ValueError("Input contains NaN, infinity or a value too large for dtype('float64').")
-    colS_h = np.ascontiguousarray(host[:-1], dtype=np.int32)
+    if lag is not None:
+        colE, colS, baseE, baseS, flags = _lag_analysis(lag, Yd, win)
+        host = torch.cat([colS, baseS, flags]).cpu().numpy()
+        if host[-2:].any():
+            raise ValueError("Input contains NaN, infinity or a value too large for dtype('float64').")
+        colS_h = np.ascontiguousarray(host[:n_aug], dtype=np.int32)
+        baseS_h = np.ascontiguousarray(host[n_aug:-2], dtype=np.int32)
+    else:
+        colE = torch.empty(n_aug, dtype=torch.int32, device="cuda")
+        colS = torch.empty(n_aug, dtype=torch.int32, device="cuda")
+        scratch = torch.empty(n_aug, dtype=torch.int64, device="cuda")
+        flag = torch.empty(1, dtype=torch.int32, device="cuda")
+        call("sglm_gram_tc_analyze_f64", ptr(Xd), row_stride(Xd), ptr(Yd), row_stride(Yd), n_y, T, C, ptr(colE),
+             ptr(colS), ptr(scratch), ptr(flag), stream_ptr())
+        host = torch.cat([colS, flag]).cpu().numpy()
+        if host[-1] != 0:
+            raise ValueError("Input contains NaN, infinity or a value too large for dtype('float64').")
+        colS_h = np.ascontiguousarray(host[:-1], dtype=np.int32)
     cells = None if TC_CELLS is False else _row_cells(set_rows, T)
     if cells is None:
         lists = [torch.arange(T, dtype=torch.int64, device="cuda") if r is None else r.to(torch.int64) for r in set_rows]
@@ -243,7 +333,12 @@ def suffstats_tc(Xd, Yd, set_rows, check_gemm=False):
     if rows.numel() == 0:
         rows = torch.full((128,), -1, dtype=torch.int64, device="cuda")
     colS_p, sizes_p = colS_h.ctypes.data_as(ctypes.c_void_p), sizes.ctypes.data_as(ctypes.c_void_p)
-    if member is None:
+    if lag is not None:
+        u0, n_u, off_h = win
+        P = int(lag.base.shape[1])
+        ws_bytes = nat.lib().sglm_gram_tc_lag_workspace_bytes(n_aug, colS_p, n_lists, sizes_p, 0 if member is None else n_sets, P,
+                                                              baseS_h.ctypes.data_as(ctypes.c_void_p), n_u)
+    elif member is None:
         ws_bytes = nat.lib().sglm_gram_tc_workspace_bytes(n_aug, colS_p, n_lists, sizes_p)
     else:
         ws_bytes = nat.lib().sglm_gram_tc_cells_workspace_bytes(n_aug, colS_p, n_lists, sizes_p, n_sets)
@@ -252,11 +347,21 @@ def suffstats_tc(Xd, Yd, set_rows, check_gemm=False):
     info = np.zeros(4, dtype=np.int64)
     nat.lib().sglm_gram_tc_plan_info(n_aug, colS_p, n_lists, sizes_p, info.ctypes.data_as(ctypes.c_void_p))
     nat.last_tc_plan = dict(S=int(info[0]), n_pos=int(info[1]), tiles=int(info[2]), k_parts=int(info[3]),
-                            planes=int(colS_h.sum()), n_aug=n_aug, row_lists=n_lists, cells=member is not None)
+                            planes=int(colS_h.sum()), n_aug=n_aug, row_lists=n_lists, cells=member is not None,
+                            lag=lag is not None)
     raw = torch.empty(ws_bytes + 1024, dtype=torch.uint8, device="cuda")
     off = (-raw.data_ptr()) % 1024
     G = _zeros((n_sets, n_aug, ldg))
-    if member is None:
+    if lag is not None:
+        bw = lag.base[u0:u0 + n_u]
+        desc = nat.LagDesignStruct(bw.data_ptr(), row_stride(bw), n_u, P, lag.src.ctypes.data, off_h.ctypes.data,
+                                   baseE.data_ptr(), baseS.data_ptr(), baseS_h.ctypes.data)
+        member_p = None if member is None else np.ascontiguousarray(member, dtype=np.int32)
+        call("sglm_gram_tc_lag_cells_f64", ctypes.byref(desc), ptr(Yd), row_stride(Yd), n_y, T, C, ptr(colE), ptr(colS), colS_p,
+             n_lists, sizes_p, ptr(rows), 0 if member is None else n_sets,
+             None if member_p is None else member_p.ctypes.data_as(ctypes.c_void_p), ptr(G), ldg,
+             ctypes.c_void_p(raw.data_ptr() + off), ws_bytes, 0, stream_ptr())
+    elif member is None:
         call("sglm_gram_tc_f64", ptr(Xd), row_stride(Xd), ptr(Yd), row_stride(Yd), n_y, T, C, ptr(colE), ptr(colS),
              colS_p, n_lists, sizes_p, ptr(rows), ptr(G), ldg, ctypes.c_void_p(raw.data_ptr() + off), ws_bytes,
              int(bool(check_gemm)), stream_ptr())
@@ -275,24 +380,46 @@ def suffstats_tc_sharded(Xd, Yd, set_rows, all_reduce):
     cuts the same digit planes, then the int64 plane Grams of the row sets (sum — exact integer arithmetic, so the
     result has the bits of the one-GPU computation).  Returns G [n_sets, n_aug, ldg], identical on every rank."""
     torch = nat.require_cuda()
+    lag = win = None
+    if isinstance(Xd, LagRecipe):
+        # every rank must take the same path: a rank whose slice reads outside the base signals (fill values) makes all
+        # ranks build their slices
+        win = Xd.window()
+        ok = torch.tensor([0 if win is None else 1], dtype=torch.int32, device="cuda")
+        all_reduce(ok, "min")
+        if int(ok.item()) == 0:
+            win = None
+            Xd = Xd.tensor()
+        else:
+            lag = Xd
     T, C = Xd.shape
     n_y = Yd.shape[1]
     n_aug = C + n_y + 1
     n_sets = len(set_rows)
     ldg = _round_up(n_aug, 8)
-    colmax = torch.empty(n_aug, dtype=torch.int64, device="cuda")
-    colS = torch.empty(n_aug, dtype=torch.int32, device="cuda")
-    colE = torch.empty(n_aug, dtype=torch.int32, device="cuda")
-    flag = torch.empty(1, dtype=torch.int32, device="cuda")
-    call("sglm_gram_tc_colstats_f64", ptr(Xd), row_stride(Xd), ptr(Yd), row_stride(Yd), n_y, T, C, ptr(colmax), ptr(colS),
-         stream_ptr())
-    all_reduce(colmax, "max")            # bits of non-negative doubles order like integers; the NaN pattern wins
-    all_reduce(colS, "min")
-    call("sglm_gram_tc_exponents", ptr(colmax), n_aug, 8, ptr(colE), ptr(colS), ptr(flag), stream_ptr())
-    host = torch.cat([colS, flag]).cpu().numpy()
-    if host[-1] != 0:
-        raise ValueError("Input contains NaN, infinity or a value too large for dtype('float64').")
-    colS_h = np.ascontiguousarray(host[:-1], dtype=np.int32)
+    if lag is not None:
+        # the analysis of the base signals, combined over the ranks: the union of the ranks' windows is the window of
+        # the one-GPU computation, so the digit planes (and the summed int64 plane Grams) are the same bits
+        colE, colS, baseE, baseS, flags = _lag_analysis(lag, Yd, win, all_reduce)
+        host = torch.cat([colS, baseS, flags]).cpu().numpy()
+        if host[-2:].any():
+            raise ValueError("Input contains NaN, infinity or a value too large for dtype('float64').")
+        colS_h = np.ascontiguousarray(host[:n_aug], dtype=np.int32)
+        baseS_h = np.ascontiguousarray(host[n_aug:-2], dtype=np.int32)
+    else:
+        colmax = torch.empty(n_aug, dtype=torch.int64, device="cuda")
+        colS = torch.empty(n_aug, dtype=torch.int32, device="cuda")
+        colE = torch.empty(n_aug, dtype=torch.int32, device="cuda")
+        flag = torch.empty(1, dtype=torch.int32, device="cuda")
+        call("sglm_gram_tc_colstats_f64", ptr(Xd), row_stride(Xd), ptr(Yd), row_stride(Yd), n_y, T, C, ptr(colmax), ptr(colS),
+             stream_ptr())
+        all_reduce(colmax, "max")            # bits of non-negative doubles order like integers; the NaN pattern wins
+        all_reduce(colS, "min")
+        call("sglm_gram_tc_exponents", ptr(colmax), n_aug, 8, ptr(colE), ptr(colS), ptr(flag), stream_ptr())
+        host = torch.cat([colS, flag]).cpu().numpy()
+        if host[-1] != 0:
+            raise ValueError("Input contains NaN, infinity or a value too large for dtype('float64').")
+        colS_h = np.ascontiguousarray(host[:-1], dtype=np.int32)
     cells = _row_cells(set_rows, T)
     if cells is None:                    # no overlap among this rank's rows: every set is its own cell
         lists = [torch.arange(T, dtype=torch.int64, device="cuda") if r is None else r.to(torch.int64) for r in set_rows]
@@ -311,7 +438,13 @@ def suffstats_tc_sharded(Xd, Yd, set_rows, all_reduce):
     if rows.numel() == 0:
         rows = torch.full((128,), -1, dtype=torch.int64, device="cuda")
     colS_p, sizes_p = colS_h.ctypes.data_as(ctypes.c_void_p), sizes.ctypes.data_as(ctypes.c_void_p)
-    ws_bytes = nat.lib().sglm_gram_tc_cells_workspace_bytes(n_aug, colS_p, n_lists, sizes_p, n_sets)
+    if lag is not None:
+        u0, n_u, off_h = win
+        P = int(lag.base.shape[1])
+        ws_bytes = nat.lib().sglm_gram_tc_lag_workspace_bytes(n_aug, colS_p, n_lists, sizes_p, n_sets, P,
+                                                              baseS_h.ctypes.data_as(ctypes.c_void_p), n_u)
+    else:
+        ws_bytes = nat.lib().sglm_gram_tc_cells_workspace_bytes(n_aug, colS_p, n_lists, sizes_p, n_sets)
     if ws_bytes == 0:
         raise nat.SglmNativeError("gram_tc: invalid plan")
     off_b, size_b = ctypes.c_uint64(0), ctypes.c_uint64(0)
@@ -320,14 +453,23 @@ def suffstats_tc_sharded(Xd, Yd, set_rows, all_reduce):
     info = np.zeros(4, dtype=np.int64)
     nat.lib().sglm_gram_tc_plan_info(n_aug, colS_p, n_lists, sizes_p, info.ctypes.data_as(ctypes.c_void_p))
     nat.last_tc_plan = dict(S=int(info[0]), n_pos=int(info[1]), tiles=int(info[2]), k_parts=int(info[3]),
-                            planes=int(colS_h.sum()), n_aug=n_aug, row_lists=n_lists, cells=cells is not None, sharded=True)
+                            planes=int(colS_h.sum()), n_aug=n_aug, row_lists=n_lists, cells=cells is not None, sharded=True,
+                            lag=lag is not None)
     raw = torch.empty(ws_bytes + 1024, dtype=torch.uint8, device="cuda")
     off = (-raw.data_ptr()) % 1024
     ws_p = ctypes.c_void_p(raw.data_ptr() + off)
     member = np.ascontiguousarray(member, dtype=np.int32)
-    call("sglm_gram_tc_cells_partial_f64", ptr(Xd), row_stride(Xd), ptr(Yd), row_stride(Yd), n_y, T, C, ptr(colE),
-         ptr(colS), colS_p, n_lists, sizes_p, ptr(rows), n_sets, member.ctypes.data_as(ctypes.c_void_p), ws_p, ws_bytes,
-         stream_ptr())
+    if lag is not None:
+        bw = lag.base[u0:u0 + n_u]
+        desc = nat.LagDesignStruct(bw.data_ptr(), row_stride(bw), n_u, P, lag.src.ctypes.data, off_h.ctypes.data,
+                                   baseE.data_ptr(), baseS.data_ptr(), baseS_h.ctypes.data)
+        call("sglm_gram_tc_lag_cells_f64", ctypes.byref(desc), ptr(Yd), row_stride(Yd), n_y, T, C, ptr(colE), ptr(colS), colS_p,
+             n_lists, sizes_p, ptr(rows), n_sets, member.ctypes.data_as(ctypes.c_void_p), None, ldg, ws_p, ws_bytes, 1,
+             stream_ptr())
+    else:
+        call("sglm_gram_tc_cells_partial_f64", ptr(Xd), row_stride(Xd), ptr(Yd), row_stride(Yd), n_y, T, C, ptr(colE),
+             ptr(colS), colS_p, n_lists, sizes_p, ptr(rows), n_sets, member.ctypes.data_as(ctypes.c_void_p), ws_p, ws_bytes,
+             stream_ptr())
     sg = raw[off + off_b.value: off + off_b.value + size_b.value].view(torch.int64)
     all_reduce(sg, "sum")
     G = _zeros((n_sets, n_aug, ldg))

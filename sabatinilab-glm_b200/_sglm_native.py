@@ -51,6 +51,9 @@ _PROTOTYPES = {
     "sglm_gram_tc_cells_workspace_bytes": (c_sz, [c_i32, c_vp, c_i32, c_vp, c_i32]),
     "sglm_gram_tc_cells_f64": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp,
                                        c_vp, c_i32, c_vp, c_vp, c_i64, c_vp, c_sz, c_i32, c_vp]),
+    "sglm_gram_tc_lag_workspace_bytes": (c_sz, [c_i32, c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_i64]),
+    "sglm_gram_tc_lag_cells_f64": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_i32,
+                                           c_vp, c_vp, c_i64, c_vp, c_sz, c_i32, c_vp]),
     "sglm_gram_tc_colstats_f64": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp]),
     "sglm_gram_tc_exponents": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "sglm_gram_tc_cells_sgout": (c_i32, [c_i32, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp]),
@@ -154,7 +157,7 @@ def ptr(t):
 
 
 # kernels launched per ABI call (for the launch count bench.py reports)
-_KERNELS_PER_CALL = {"sglm_suffstats_f64": 3, "sglm_gram_tc_analyze_f64": 3, "sglm_gram_tc_f64": 3, "sglm_gram_tc_cells_f64": 4, "sglm_gram_tc_cells_partial_f64": 3, "sglm_gram_tc_scaled_f64": 3, "sglm_gram_tc_analyze_scaled_f64": 2, "sglm_xt_vec_f64": 2, "sglm_score_f64": 2, "sglm_poisson_irls_prepare_f64": 2,
+_KERNELS_PER_CALL = {"sglm_suffstats_f64": 3, "sglm_gram_tc_analyze_f64": 3, "sglm_gram_tc_f64": 3, "sglm_gram_tc_cells_f64": 4, "sglm_gram_tc_lag_cells_f64": 6, "sglm_gram_tc_cells_partial_f64": 3, "sglm_gram_tc_scaled_f64": 3, "sglm_gram_tc_analyze_scaled_f64": 2, "sglm_xt_vec_f64": 2, "sglm_score_f64": 2, "sglm_poisson_irls_prepare_f64": 2,
                      "sglm_timeshift_f64": 2, "sglm_pb_xt_r_f64": 2, "sglm_pb_epilogue_f64": 2, "sglm_pb_step_f64": 3,
                      "sglm_lag_valid_rows": 3, "sglm_col_moments_f64": 4, "sglm_mask_compact_rows": 3}
 _timing = None         # when enabled: list of (name, start_event, end_event) on the current stream
@@ -229,6 +232,13 @@ def call(name, *args):
 
 def launches():
     return _launches
+
+
+class LagDesignStruct(ctypes.Structure):
+    """sglm_lag_design of include/sglm_b200.h."""
+    _fields_ = [("base", ctypes.c_void_p), ("ldb", ctypes.c_int64), ("n_u", ctypes.c_int64), ("P", ctypes.c_int32),
+                ("src_host", ctypes.c_void_p), ("off_host", ctypes.c_void_p), ("baseE", ctypes.c_void_p),
+                ("baseS", ctypes.c_void_p), ("baseS_host", ctypes.c_void_p)]
 
 
 NAN_BITS = int(np.array([np.nan], dtype=np.float64).view(np.uint64)[0])

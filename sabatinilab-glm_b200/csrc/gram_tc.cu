@@ -137,8 +137,9 @@ __global__ void __launch_bounds__(256)
 tc_slice_kernel(const double *__restrict__ X, long long ldx, const double *__restrict__ Y, long long ldy,
                 int C, int n_y, const double *__restrict__ rs, const long long *__restrict__ rows, long long n_pos,
                 const int *__restrict__ colE, const int *__restrict__ colS, const int *__restrict__ plane_row,
-                int8_t *__restrict__ At, long long ld_at) {
+                int8_t *__restrict__ At, long long ld_at, long long n_ident) {
     // plane_row[c * TC_SMAX + (k-1)] = row of At holding digit plane k of column c (or -1)
+    // rows == nullptr: position p is row p for p < n_ident (the base signals of a lag design, sliced once)
     __shared__ __align__(16) double tile[32][130];        // [column][position], transposed on the way in
     const int n_aug = C + n_y + 1;
     const long long p0 = (long long)blockIdx.x * 128;
@@ -147,7 +148,7 @@ tc_slice_kernel(const double *__restrict__ X, long long ldx, const double *__res
     // the 128 row indices first (one coalesced load), so that the 16 element loads of a thread below do not
     // each wait for their own index: 16 independent loads in flight per thread
     __shared__ long long srow[128];
-    if (tid < 128) srow[tid] = (p0 + tid < n_pos) ? rows[p0 + tid] : -1;
+    if (tid < 128) srow[tid] = (p0 + tid < n_pos) ? (rows ? rows[p0 + tid] : (p0 + tid < n_ident ? p0 + tid : -1)) : -1;
     __syncthreads();
     // load 128 positions x 32 columns, coalesced along the columns of the row-major source
     {
@@ -191,6 +192,50 @@ tc_slice_kernel(const double *__restrict__ X, long long ldx, const double *__res
                                   (((unsigned)(int)d2 & 0xffu) << 16) | (((unsigned)(int)d3 & 0xffu) << 24);
             *reinterpret_cast<unsigned *>(At + (long long)plane_row[c * TC_SMAX + (k - 1)] * ld_at + p) = pack;
         }
+    }
+}
+
+// ------------------------------------------------------------------ lag designs: planes of the design from planes of the base
+// A lag design column (base signal p, shift s) is the base signal read at another row:  Z[t, c] = base[t + off_c, p].
+// Its digit planes are therefore the base signal's planes read at another position — the fp64 design is never
+// built or read: the base signals (P columns instead of P*L) are sliced once into Bt, and the K-major operand
+// At[(plane k of column c)][pos] = Bt[(plane k of p_c)][rows[pos] + off_c] is a byte gather (reads hit L1 / L2: the L
+// shifts of a signal read the same bytes; HBM traffic = the write of At).  map[r] = (row of Bt, off) of At row r,
+// (-1, .) for rows that are not lag columns (response / ones planes, padding between levels).
+constexpr int TC_EXP_ROWS = 512;     // At rows per CTA (blockIdx.y)
+__global__ void __launch_bounds__(256)
+tc_expand_kernel(const int8_t *__restrict__ Bt, long long ld_bt, const long long *__restrict__ rows, long long n_pos,
+                 const int2 *__restrict__ map, int n_at_rows, int8_t *__restrict__ At, long long ld_at) {
+    __shared__ long long srow[128];
+    const int tid = threadIdx.x;
+    const long long p0 = (long long)blockIdx.x * 128;
+    if (tid < 128) srow[tid] = (p0 + tid < n_pos) ? rows[p0 + tid] : -1;
+    __syncthreads();
+    const int pq = tid & 31, rl = tid >> 5;
+    const long long p = p0 + 4 * pq;
+    if (p >= n_pos) return;
+    const long long r0 = srow[4 * pq], r1 = srow[4 * pq + 1], r2 = srow[4 * pq + 2], r3 = srow[4 * pq + 3];
+    const bool contig = r0 >= 0 && r1 == r0 + 1 && r2 == r0 + 2 && r3 == r0 + 3;
+    const int r_end = min(n_at_rows, (int)(blockIdx.y + 1) * TC_EXP_ROWS);
+    for (int r = blockIdx.y * TC_EXP_ROWS + rl; r < r_end; r += 8) {
+        const int2 m = map[r];
+        if (m.x < 0) continue;
+        const int8_t *src = Bt + (long long)m.x * ld_bt + m.y;
+        unsigned pack;
+        if (contig) {
+            // four consecutive bytes at an arbitrary byte offset: two aligned words and a funnel shift
+            const unsigned long long a = (unsigned long long)(src + r0);
+            const unsigned *w = reinterpret_cast<const unsigned *>(a & ~3ull);
+            const unsigned sh = (unsigned)(a & 3ull) * 8u;
+            const unsigned lo = __ldg(w);
+            const unsigned hi = sh ? __ldg(w + 1) : 0u;
+            pack = __funnelshift_r(lo, hi, sh);
+        } else {
+            const unsigned b0 = r0 >= 0 ? (unsigned char)__ldg(src + r0) : 0u, b1 = r1 >= 0 ? (unsigned char)__ldg(src + r1) : 0u;
+            const unsigned b2 = r2 >= 0 ? (unsigned char)__ldg(src + r2) : 0u, b3 = r3 >= 0 ? (unsigned char)__ldg(src + r3) : 0u;
+            pack = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+        }
+        *reinterpret_cast<unsigned *>(At + (long long)r * ld_at + p) = pack;
     }
 }
 
@@ -693,6 +738,26 @@ static TcLayout tc_layout(const TcPlan &p, int n_out = 0) {
     return L;
 }
 
+// Lag designs (sglm_lag_design): digit planes of the base signals [base | 1] (consecutive rows of Bt, no level padding)
+// and the extra workspace behind the ordinary layout: Bt, its plane table, the (row of Bt, offset) map of At's rows.
+static void tc_lag_base_planes(int P, const int *baseS_host, std::vector<int> &bplane, int &nb) {
+    bplane.assign((size_t)(P + 1) * TC_SMAX, -1);
+    nb = 0;
+    for (int q = 0; q <= P; ++q)
+        for (int k = 0; k < std::min(std::max(baseS_host[q], 1), TC_SMAX); ++k) bplane[(size_t)q * TC_SMAX + k] = nb++;
+}
+struct TcLagLayout { size_t off_bt, off_bplane, off_map, total; long long ld_bt; };
+static TcLagLayout tc_lag_layout(size_t base_total, int nb, int P, long long n_u, long long S) {
+    TcLagLayout LL;
+    LL.ld_bt = (std::max<long long>(n_u, 1) + 127) / 128 * 128;
+    size_t o = tc_align(base_total);
+    LL.off_bt = o; o += tc_align((size_t)nb * LL.ld_bt + 1024);
+    LL.off_bplane = o; o += tc_align((size_t)(P + 1) * TC_SMAX * sizeof(int));
+    LL.off_map = o; o += tc_align((size_t)S * sizeof(int2));
+    LL.total = o;
+    return LL;
+}
+
 // Pass 1: per-column exponent and number of digit planes (device arrays colE, colS of n_aug int32;
 // colmax_scratch: n_aug uint64; flag: 1 int32, set when the data contain NaN/inf).
 static int gram_tc_analyze(const double *X, int64_t ldx, const double *Y, int64_t ldy, int32_t n_y, int64_t T,
@@ -811,7 +876,8 @@ static int gram_tc_run(const double *X, int64_t ldx, const double *Y, int64_t ld
                        int32_t C, const int32_t *colE, const int32_t *colS, const int32_t *colS_host,
                        int32_t n_sets, const int64_t *set_rows_host, const int64_t *rows, int32_t n_out,
                        const int32_t *member_host, double *G, int64_t ldg, void *workspace, size_t workspace_bytes,
-                       int32_t use_check_gemm, void *stream, const double *rs = nullptr, int stage = 0);
+                       int32_t use_check_gemm, void *stream, const double *rs = nullptr, int stage = 0,
+                       const sglm_lag_design *lag = nullptr);
 
 extern "C" int sglm_gram_tc_f64(const double *X, int64_t ldx, const double *Y, int64_t ldy, int32_t n_y, int64_t T,
                                 int32_t C, const int32_t *colE, const int32_t *colS, const int32_t *colS_host,
@@ -895,11 +961,42 @@ extern "C" int sglm_gram_tc_cells_combine_f64(int32_t C, int32_t n_y, const int3
                        n_out, nullptr, G, ldg, workspace, workspace_bytes, 0, stream, nullptr, 2);
 }
 
+// Lag designs: the same statistics WITHOUT the design matrix (see tc_expand_kernel).  n_out == 0: the row lists are
+// the sets themselves; n_out > 0: cells + membership as in sglm_gram_tc_cells_f64.  partial != 0: stop after the
+// int64 plane Grams (row-sharded use; finish with sglm_gram_tc_cells_combine_f64 — the ordinary part of the
+// workspace has the ordinary layout).
+extern "C" size_t sglm_gram_tc_lag_workspace_bytes(int32_t n_aug, const int32_t *colS_host, int32_t n_cells,
+                                                   const int64_t *cell_rows_host, int32_t n_out, int32_t P,
+                                                   const int32_t *baseS_host, int64_t n_u) {
+    if (n_aug <= 0 || n_cells <= 0 || n_out < 0 || !colS_host || !cell_rows_host || P <= 0 || !baseS_host || n_u < 0) return 0;
+    TcPlan p;
+    tc_make_plan(n_aug, colS_host, n_cells, (const long long *)cell_rows_host, p);
+    std::vector<int> bplane;
+    int nb = 0;
+    tc_lag_base_planes(P, baseS_host, bplane, nb);
+    return tc_lag_layout(tc_layout(p, n_out).total, nb, P, n_u, p.S).total;
+}
+
+extern "C" int sglm_gram_tc_lag_cells_f64(const sglm_lag_design *lag, const double *Y, int64_t ldy, int32_t n_y, int64_t T,
+                                          int32_t C, const int32_t *colE, const int32_t *colS, const int32_t *colS_host,
+                                          int32_t n_cells, const int64_t *cell_rows_host, const int64_t *rows,
+                                          int32_t n_out, const int32_t *member_host, double *G, int64_t ldg,
+                                          void *workspace, size_t workspace_bytes, int32_t partial, void *stream) {
+    SGLM_CHECK_ARG(lag != nullptr, SGLM_E_INVALID_ARG, "gram_tc_lag_cells: null lag design");
+    SGLM_CHECK_ARG(n_out == 0 || member_host, SGLM_E_INVALID_ARG, "gram_tc_lag_cells: membership table missing");
+    SGLM_CHECK_ARG(n_out == 0 || n_cells <= TC_SUM_CELLS, SGLM_E_UNSUPPORTED, "gram_tc_lag_cells: at most %d cells", TC_SUM_CELLS);
+    SGLM_CHECK_ARG(!partial || n_out > 0, SGLM_E_INVALID_ARG, "gram_tc_lag_cells: the partial form needs output sets");
+    double dummy;
+    return gram_tc_run(nullptr, C, Y, ldy, n_y, T, C, colE, colS, colS_host, n_cells, cell_rows_host, rows, n_out,
+                       member_host, partial ? &dummy : G, partial ? (int64_t)(C + n_y + 1) : ldg, workspace, workspace_bytes, 0,
+                       stream, nullptr, partial ? 1 : 0, lag);
+}
+
 static int gram_tc_run(const double *X, int64_t ldx, const double *Y, int64_t ldy, int32_t n_y, int64_t T,
                        int32_t C, const int32_t *colE, const int32_t *colS, const int32_t *colS_host,
                        int32_t n_sets, const int64_t *set_rows_host, const int64_t *rows, int32_t n_out,
                        const int32_t *member_host, double *G, int64_t ldg, void *workspace, size_t workspace_bytes,
-                       int32_t use_check_gemm, void *stream, const double *rs, int stage) {
+                       int32_t use_check_gemm, void *stream, const double *rs, int stage, const sglm_lag_design *lag) {
     const int n_aug = C + n_y + 1;
     SGLM_CHECK_ARG(T >= 0 && C >= 0 && n_y >= 0 && n_sets >= 1 && ldx >= C && ldy >= n_y && ldg >= n_aug, SGLM_E_SHAPE,
                    "gram_tc: bad shape");
@@ -952,12 +1049,56 @@ static int gram_tc_run(const double *X, int64_t ldx, const double *Y, int64_t ld
     }
     if (n_out > 0)
         SGLM_CUDA_OK(cudaMemcpyAsync(d_member, member_host, (size_t)n_out * n_sets * sizeof(int), cudaMemcpyHostToDevice, st));
+    TcLagLayout LL = {};
+    std::vector<int> bplane;
+    std::vector<int2> lag_map;
+    if (lag) {
+        // lag design: planes of the base signals + the map (row of Bt, row offset) of every plane row of At
+        SGLM_CHECK_ARG(rs == nullptr, SGLM_E_UNSUPPORTED, "gram_tc: row scales are not supported for lag designs");
+        SGLM_CHECK_ARG(lag->base && lag->src_host && lag->off_host && lag->baseE && lag->baseS && lag->baseS_host &&
+                       lag->P > 0 && lag->ldb >= lag->P && lag->n_u >= T, SGLM_E_INVALID_ARG, "gram_tc: bad lag design");
+        int nb = 0;
+        tc_lag_base_planes(lag->P, lag->baseS_host, bplane, nb);
+        LL = tc_lag_layout(L.total, nb, lag->P, lag->n_u, p.S);
+        SGLM_CHECK_ARG(workspace_bytes >= LL.total, SGLM_E_WORKSPACE, "gram_tc: workspace too small for the lag design (%zu < %zu)",
+                       workspace_bytes, LL.total);
+        lag_map.assign((size_t)p.S, make_int2(-1, 0));
+        for (int c = 0; c < C; ++c) {
+            const int pc = lag->src_host[c], off = lag->off_host[c];
+            SGLM_CHECK_ARG(pc >= 0 && pc < lag->P && off >= 0 && (long long)off + T <= lag->n_u, SGLM_E_INVALID_ARG,
+                           "gram_tc: lag column %d reads outside the base window", c);
+            for (int k = 0; k < colS_host[c]; ++k) {
+                const int r = p.plane_row[(size_t)c * TC_SMAX + k], b = bplane[(size_t)pc * TC_SMAX + k];
+                SGLM_CHECK_ARG(r >= 0 && b >= 0, SGLM_E_INVALID_ARG, "gram_tc: lag column %d has more planes than its base signal", c);
+                lag_map[(size_t)r] = make_int2(b, off);
+            }
+        }
+        SGLM_CUDA_OK(cudaMemcpyAsync(ws + LL.off_bplane, bplane.data(), bplane.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        SGLM_CUDA_OK(cudaMemcpyAsync(ws + LL.off_map, lag_map.data(), lag_map.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+    }
     SGLM_CUDA_OK(cudaStreamSynchronize(st));        // the pageable host vectors above die with this frame
 
+    if (lag) {
+        int8_t *Bt = (int8_t *)(ws + LL.off_bt);
+        dim3 bgrid((unsigned)(LL.ld_bt / 128), (unsigned)ceil_div(lag->P + 1, 32));
+        tc_slice_kernel<<<bgrid, 256, 0, st>>>(lag->base, lag->ldb, nullptr, 0, lag->P, 0, nullptr, nullptr, LL.ld_bt, lag->baseE,
+                                               lag->baseS, (const int *)(ws + LL.off_bplane), Bt, LL.ld_bt, lag->n_u);
+        SGLM_LAUNCH_OK("tc_slice_kernel(base)");
+        dim3 egrid((unsigned)(p.n_pos / 128), (unsigned)ceil_div((int)p.S, TC_EXP_ROWS));
+        tc_expand_kernel<<<egrid, 256, 0, st>>>(Bt, LL.ld_bt, (const long long *)rows, p.n_pos, (const int2 *)(ws + LL.off_map),
+                                                (int)p.S, At, p.n_pos);
+        SGLM_LAUNCH_OK("tc_expand_kernel");
+        // response columns and the ones column: sliced from Y as before
+        dim3 ygrid((unsigned)(p.n_pos / 128), (unsigned)ceil_div(n_y + 1, 32));
+        tc_slice_kernel<<<ygrid, 256, 0, st>>>(nullptr, 0, Y, ldy, 0, n_y, nullptr, (const long long *)rows, p.n_pos, colE + C,
+                                               colS + C, d_plane + (size_t)C * TC_SMAX, At, p.n_pos, 0);
+        SGLM_LAUNCH_OK("tc_slice_kernel(y)");
+    } else {
     dim3 sgrid((unsigned)(p.n_pos / 128), (unsigned)ceil_div(n_aug, 32));
     tc_slice_kernel<<<sgrid, 256, 0, st>>>(X, ldx, Y, ldy, C, n_y, rs, (const long long *)rows, p.n_pos, colE, colS,
-                                           d_plane, At, p.n_pos);
+                                           d_plane, At, p.n_pos, 0);
     SGLM_LAUNCH_OK("tc_slice_kernel");
+    }
 
     const int n_tiles = (int)p.tiles.size();
     if (use_check_gemm) {

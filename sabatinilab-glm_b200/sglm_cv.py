@@ -216,10 +216,13 @@ class GaussianSession:
         T, C, F = self.T, self.C, self.F
         tr_w, te_w = self.fold_sets()
         if G is None and not self.extra and _use_tensor_core_gram(T, C):
-            # 0/1 row sets: tcgen05 int8 digit-plane Gram (exact integer accumulation, fp64 result)
+            # 0/1 row sets: tcgen05 int8 digit-plane Gram (exact integer accumulation, fp64 result); a lag design that
+            # is still a recipe (eng.LagRecipe) gets its digit planes from the base signals — it is never built
             test_rows = _unique_sorted_rows(self.cv_idx, T)
             if test_rows is not None:
                 G, _ = eng.suffstats_tc(self.Xd, self.Yd, [None] + test_rows)
+        if G is None and isinstance(self.Xd, eng.LagRecipe):
+            self.Xd = self.Xd.tensor()
         if G is None:
             # general row multiplicities: fp64 DMMA Gram with row weights (at most 64 row sets per launch)
             w_rows = [None] + te_w + [tr_w[f] for f in self.extra]
@@ -421,7 +424,7 @@ def cv_glm_mult_params_sessions(sessions, model_name, glm_kwarg_lst, verbose=0, 
             kw = dict(glm_kwargs)
             name = kw.pop('model_name', model_name if model_name is not None else 'Gaussian')
             entries.append((name, kw))
-        Xd, yd = eng.device_matrix(X), eng.device_vector(y)
+        Xd, yd = eng.device_design(X), eng.device_vector(y)
         if Xd.shape[0] != yd.shape[0]:
             raise ValueError(f"Found input variables with inconsistent numbers of samples: [{Xd.shape[0]}, {yd.shape[0]}]")
         cv = _normalise_cv_idx(list(cv_idx), Xd.shape[0])
@@ -539,7 +542,7 @@ def _poisson_grid(Xd, yd, cv_idx, glms, rolls, score_method):
 
 
 def _cv_batch(X, y, cv_idx, entries, beta_, beta0_, score_method):
-    Xd = eng.device_matrix(X)
+    Xd = eng.device_design(X)          # a contiguous device-resident lag design stays a recipe (never built)
     yd = eng.device_vector(y)
     if Xd.shape[0] != yd.shape[0]:
         raise ValueError(f"Found input variables with inconsistent numbers of samples: [{Xd.shape[0]}, {yd.shape[0]}]")
@@ -556,6 +559,8 @@ def _cv_batch(X, y, cv_idx, entries, beta_, beta0_, score_method):
         for i, r in zip(gauss, res):
             out[i] = r
     if pois:
+        if isinstance(Xd, eng.LagRecipe):
+            Xd = Xd.tensor()
         res = _poisson_grid(Xd, yd, cv_idx, [glms[i] for i in pois], [rolls[i] for i in pois], score_method)
         for i, r in zip(pois, res):
             out[i] = r

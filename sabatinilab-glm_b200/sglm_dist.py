@@ -277,11 +277,10 @@ def cv_grid_strong(X0, shift_amt_list, y, cv_idx, model_name, glm_kwarg_lst, ver
 
     # ---- this rank's rows of the design: valid rows [g0, g1), gathered from the base rows they reach
     g0, g1 = n * rank // world, n * (rank + 1) // world
-    a, b = max(0, lo + g0 - smax), min(T, lo + g1 - smin)
     src_cols, sh_cols, _ = sglm_pp.build_column_map(P, shift_inx, shifts)
-    local = eng.gather(X0d[a:b], src_cols, sh_cols, fill_value)
-    off = lo + g0 - a
-    Xd = local[off: off + (g1 - g0)]
+    # ... as a recipe: the statistics come from the base signals (eng.LagRecipe), the slice of the design is only built
+    # when a column reads outside the base signals
+    Xd = eng.LagRecipe(X0d, src_cols, sh_cols, lo + g0, lo + g1, fill_value)
     C = Xd.shape[1]
     mark("gather")
 
@@ -311,7 +310,7 @@ def cv_grid_strong(X0, shift_amt_list, y, cv_idx, model_name, glm_kwarg_lst, ver
 
     G = eng.suffstats_tc_sharded(Xd, Yd, [None] + local_tests, all_reduce)
     mark("statistics")
-    del local, Xd
+    del Xd
 
     ses = sglm_cv.GaussianSession.from_statistics(G, n, C, yd, n_te, glms, rolls, score_method)
     models = ses.model_specs()

@@ -223,6 +223,15 @@ class DeviceDesign:
     def copy(self):
         return self._derive()
 
+    def lag_recipe(self):
+        """The design as an engine-level recipe (base signals + column map + contiguous row range) when its rows
+        ARE a contiguous range — then the CV grid computes its statistics from the base signals and the design is
+        never built; None otherwise (row lists after an interior NaN: the gathered tensor is used)."""
+        if self._rows is not None and not isinstance(self._rows, tuple):
+            return None
+        lo, hi = (0, self._T) if self._rows is None else self._rows
+        return eng.LagRecipe(self._base, self._src, self._sh, lo, hi, self._fill, cache=self._cache)
+
     # ---- materialisation
     def tensor(self):
         """The design as a CUDA float64 tensor [rows, C] (built once, cached): plain gather + row view when
@@ -309,6 +318,8 @@ def timeshift_multiple(X, shift_inx=[], shift_amt_list=[-1, 0, 1], unshifted_kee
     if len(shift_amt_list) == 0:
         raise ValueError("need at least one array to concatenate")
     if eng.is_torch(X):
+        if device:         # CUDA tensor in, lazy device-resident design out (explicit opt-in only)
+            return DeviceDesign(eng.device_matrix(X), src, sh, fill_value, None, None)
         return eng.gather(eng.device_matrix(X), src, sh, fill_value)
     if device is None:
         device = _device_default()
