@@ -118,7 +118,12 @@ def config_dict(args, n_gpus, mode):
             "T": args.T, "C": C, "folds": args.folds, "alphas": args.alphas, "l1_ratios": args.l1s,
             "fits_per_step": len(grid) * (args.folds + 1), "mode": mode,
             "sessions": n_gpus * spg if mode == "sessions" else 1,
-            "l2_policy": "inputs larger than L2 (design matrix %.1f GB >> 126 MB)" % (args.T * C * 8 / 1e9)}
+            "l2_policy": ("inputs and working set larger than L2: base signals %.2f GB in, int8 digit planes of the %.0f GB design "
+                          "(~%.1f GB) written and re-read by the Gram GEMM, 6 x %.0f MB centred statistics streamed by coordinate "
+                          "descent (126 MB L2); the fp64 design itself is never built on the statistics path"
+                          % (args.T * args.P * 8 / 1e9, args.T * C * 8 / 1e9, args.T * C * 2.4 / 1e9, C * C * 8 / 1e6)),
+            "host": "Python cyclic GC frozen after the warm-up steps (gc.freeze): a generation-2 pass over the interpreter's "
+                    "module objects is ~50 ms of host time"}
 
 
 # --------------------------------------------------------------------------- #
@@ -134,7 +139,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("BENCH_SAMPLER_MS", "200")],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -402,6 +407,22 @@ def main():
         probes = measure_probes(nat, torch)
     for _ in range(args.warmup):
         res = step_device()
+    # Python's cyclic collector: a generation-2 pass walks every live object of the interpreter (torch, pandas, scipy
+    # modules: ~50 ms, measured with gc.callbacks) and lands in a timed step now and then.  Objects alive after the
+    # warm-up are moved to the permanent generation, so later passes only walk what the steps themselves allocate.
+    import gc
+    gc.collect()
+    gc.freeze()
+    gc_log = []
+    if os.environ.get("BENCH_GAPS"):
+        t_gc = [0.0]
+
+        def _gc_cb(phase, info):
+            if phase == "start":
+                t_gc[0] = time.perf_counter()
+            else:
+                gc_log.append((info.get("generation"), round((time.perf_counter() - t_gc[0]) * 1e3, 2)))
+        gc.callbacks.append(_gc_cb)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -412,6 +433,18 @@ def main():
     _engine.cd_parts_log.clear()
     total_ms, res = timed(step_device, args.steps)
     per_entry = nat.collect_timing()
+    if rank == 0 and os.environ.get("BENCH_GAPS"):
+        # diagnostics: where the stream idles between ABI calls (host work, read-backs, torch glue)
+        iv = sorted(nat.last_intervals, key=lambda t: t[1])
+        gaps, prev_end, prev_name = [], 0.0, "start"
+        for name, a, b in iv:
+            if a - prev_end > 0.5:
+                gaps.append((round(a - prev_end, 2), prev_name, name, round(a, 1)))
+            if b > prev_end:
+                prev_end, prev_name = b, name
+        sys.stderr.write(f"[gc] collections during the timed steps (generation, ms): {[g for g in gc_log if g[1] > 0.5]}\n")
+        sys.stderr.write(f"[gaps] total {total_ms:.1f} ms, last call ends {prev_end:.1f} ms after the first; gaps > 0.5 ms: "
+                         f"{sorted(gaps, reverse=True)[:12]}\n")
     cd_parts_stats = _engine.cd_stats()
     _engine.CD_COLLECT_STATS = False
     nat.enable_timing(False)

@@ -178,6 +178,8 @@ def collect_timing():
     if _timing:
         torch.cuda.synchronize()
         ref = _timing[0][1]
+        global _first_event
+        _first_event = ref
         last_intervals = []
         for name, e0, e1 in _timing:
             c, t = out.get(name, (0, 0.0))
@@ -188,6 +190,7 @@ def collect_timing():
     return out
 
 
+_first_event = None
 last_intervals = []     # (entry point, start ms, end ms) of the calls of the last collect_timing(), relative to its first call
 
 

@@ -386,15 +386,31 @@ class GaussianSession:
                 raise np.linalg.LinAlgError("Matrix is singular: X'X + alpha*I is not positive definite")
         return results
 
-    def download_and_assemble(self, Wd, b_d, rss_test, rss_train, info, status):
+    def download_coefficients(self, Wd, ready=None):
         """Coefficients leave the device already in the layout of the result dicts: [set][C][F] for the folds
         (cv_coefs is C x F, backend/sglm_cv.py:98) and [set][C] for the refits — one transposition on the device
-        instead of one per parameter set on the host."""
+        instead of one per parameter set on the host.  With `ready` (an event recorded when Wd was complete) the
+        transposition and the copies run on a side stream, next to whatever the caller has queued on the current
+        stream since (the score kernels)."""
+        import torch
         C, F = self.C, self.F
         n_sets_k = len(self.glms)
-        W3 = Wd[:, :C].reshape(n_sets_k, F + 1, C)
-        coef_folds = W3[:, :F, :].permute(0, 2, 1).contiguous().cpu().numpy()      # [set][C][F]
-        coef_full = W3[:, F, :].contiguous().cpu().numpy()                          # [set][C]
+
+        def fetch():
+            W3 = Wd[:, :C].reshape(n_sets_k, F + 1, C)
+            return (W3[:, :F, :].permute(0, 2, 1).contiguous().cpu().numpy(),         # [set][C][F]
+                    W3[:, F, :].contiguous().cpu().numpy())                            # [set][C]
+        if ready is None:
+            return fetch()
+        side = eng._side_stream(200)
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            out = fetch()                                   # .cpu() waits for the side stream only
+        Wd.record_stream(side)
+        return out
+
+    def download_and_assemble(self, Wd, b_d, rss_test, rss_train, info, status, coefs=None):
+        coef_folds, coef_full = self.download_coefficients(Wd) if coefs is None else coefs
         return self.assemble(coef_folds, coef_full, b_d.cpu().numpy(), rss_test.cpu().numpy(),
                              rss_train.cpu().numpy(), info, status)
 
@@ -405,9 +421,13 @@ def _gaussian_grid(Xd, yd, cv_idx, glms, rolls, score_method):
     ses = GaussianSession(Xd, yd, cv_idx, glms, rolls, score_method)
     ses.build_statistics()
     models = ses.model_specs()
+    import torch
     Wd, info, status = eng.solve_models(models, ses.C)
-    b_d, _, rss_test, rss_train = ses.score(Wd)
-    return ses.download_and_assemble(Wd, b_d, rss_test, rss_train, info, status)
+    ready = torch.cuda.Event()
+    ready.record()
+    b_d, _, rss_test, rss_train = ses.score(Wd)              # queued; the coefficients travel meanwhile
+    coefs = ses.download_coefficients(Wd, ready)
+    return ses.download_and_assemble(Wd, b_d, rss_test, rss_train, info, status, coefs)
 
 
 def cv_glm_mult_params_sessions(sessions, model_name, glm_kwarg_lst, verbose=0, score_method='mse'):

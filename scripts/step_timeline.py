@@ -17,14 +17,15 @@ folds = [(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()) for a, b in sy
 grid = [dict(alpha=float(a), l1_ratio=float(l), max_iter=1000, fit_intercept=True, tol=1e-4)
         for l in np.linspace(0.1, 0.9, 5) for a in np.logspace(-4, 0, 50)]
 def step():
-    dd = sglm_pp.timeshift_multiple(X0, shift_amt_list=shifts)
-    return sglm_cv.cv_glm_mult_params(dd[29:T - 20], y, folds, "Gaussian", [dict(g) for g in grid], score_method="r2")
+    dd = sglm_pp.timeshift_multiple(X0, shift_amt_list=shifts, device=True).dropna()
+    return sglm_cv.cv_glm_mult_params(dd, y, folds, "Gaussian", [dict(g) for g in grid], score_method="r2")
 step(); step(); torch.cuda.synchronize()
 nat.enable_timing(True); nat.collect_timing()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); step(); e1.record(); torch.cuda.synchronize()
 nat.collect_timing()
 print(f"step {e0.elapsed_time(e1):.1f} ms")
+print("first call starts", f"{e0.elapsed_time(nat._first_event):.2f} ms after the step's start event" if getattr(nat, "_first_event", None) is not None else "")
 prev = 0.0
 for name, a, b in sorted(nat.last_intervals, key=lambda t: t[1]):
     print(f"{a:8.2f} -> {b:8.2f}  ({b - a:7.2f} ms, gap before {a - prev:6.2f})  {name}")
