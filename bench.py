@@ -274,6 +274,14 @@ def measure_probes(nat, torch):
 
 def main():
     args = parse_args()
+    # stdout carries exactly ONE JSON line: everything else written to file descriptor 1 by libraries (NCCL prints its
+    # version banner there) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -297,7 +305,7 @@ def main():
                                  "sample_value": v_sample},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -432,6 +440,7 @@ def main():
     _engine.CD_COLLECT_STATS = True
     _engine.cd_parts_log.clear()
     total_ms, res = timed(step_device, args.steps)
+    device_timeline = dict(getattr(sglm_dist, "last_timeline", None) or {}) if strong else None
     per_entry = nat.collect_timing()
     if rank == 0 and os.environ.get("BENCH_GAPS"):
         # diagnostics: where the stream idles between ABI calls (host work, read-backs, torch glue)
@@ -471,6 +480,14 @@ def main():
     # light model) are launched on two streams and overlap, so the time they cover together is what counts
     cd_names = ("sglm_enet_cd_cluster_f64", "sglm_enet_cd_gram_f64")
     cd_part_ms = {n: k_ms.pop(n) for n in cd_names if n in k_ms}
+    # per LAUNCH of a step (a plan may hold several cluster launches): launch order inside a step = plan order
+    cd_launch_ms = []
+    for n in cd_names:
+        iv = sorted((a, b) for nm, a, b in nat.last_intervals if nm == n)
+        per_step = len(iv) // max(1, args.steps)
+        for j in range(per_step):
+            sel = iv[j::per_step] if per_step else []
+            cd_launch_ms.append((n, j, sum(b - a for a, b in sel) / max(1, len(sel))))
     CD = "sglm_enet_cd (cluster + per-model parts, concurrent)" if len(cd_part_ms) > 1 else next(iter(cd_part_ms), cd_names[0])
     if cd_part_ms:
         k_ms[CD] = nat.union_ms(cd_names) / args.steps
@@ -508,14 +525,21 @@ def main():
     heaviest = max((p for p in cd_parts_stats), key=lambda p: p["max_blocks_one_model"], default=None)
     chain = None
     if heaviest:
-        part_ms = cd_part_ms.get("sglm_enet_cd_cluster_f64" if heaviest["shape"] != "0x0" else "sglm_enet_cd_gram_f64", float("nan"))
+        # the launch that holds the heaviest model: cluster launches are logged in plan order, the per-model launch last
+        cl = [p for p in cd_parts_stats[:max(1, len(cd_parts_stats) // max(1, args.steps))] if p["shape"] != "0x0"]
+        if heaviest["shape"] != "0x0":
+            j = next((k for k, p in enumerate(cl) if p["shape"] == heaviest["shape"]), 0)
+            part_ms = next((ms for n, jj, ms in cd_launch_ms if n == "sglm_enet_cd_cluster_f64" and jj == j), float("nan"))
+        else:
+            part_ms = next((ms for n, jj, ms in cd_launch_ms if n == "sglm_enet_cd_gram_f64"), float("nan"))
         chain = {"heaviest_model_blocks": heaviest["max_blocks_one_model"], "heaviest_model_sweeps": heaviest["max_sweeps"],
                  "its_part": heaviest["shape"], "its_part_ms": part_ms,
                  "us_per_block_if_chain_bound": part_ms * 1e3 / max(1.0, heaviest["max_blocks_one_model"]),
                  "register_phase_share_of_that_model": heaviest["register_phase_share_heaviest"],
                  "note": "a model is a serial chain of 32-coordinate blocks (register phase -> record -> panel); the "
                          "part's time / the longest chain = us per block the heaviest model would need if it alone "
-                         "bounded the part (measured alone: 3.4 us on 1x8, 4.3 us on 4x2, profiles/r1_cd_cluster.txt)"}
+                         "bounded the part (measured under load: 4.0 us on (4,4), 6.1 us on (4,2), profiles/r2_cd_experiments.txt); "
+                         "its_part_ms = duration of the launch that holds it (launches of a plan overlap)"}
     rooflines = {}
     l2_peak = probes["l2_read_gbs"] if probes else None
     cd_traffic = dram_traffic("sglm_enet_cd", n_upd)
@@ -528,6 +552,7 @@ def main():
                      "coordinate_updates_per_step": n_upd, "sweeps_total": n_sweeps, "models_not_converged": n_unconv,
                      "algorithmic_GBps_one_model_at_a_time": (n_upd * 8.0 * C + n_sweeps * 8.0 * 5 * C) / cd_sec / 1e9,
                      "chain": chain, "parts": cd_parts_stats, "parts_ms_per_step": cd_part_ms,
+                     "launch_ms": [{"entry": n, "launch_in_step": j, "ms": ms} for n, j, ms in cd_launch_ms],
                      "plan": _engine._cd_plan(C, fits_per_step if not strong else -(-fits_per_step // world), args.folds + 1),
                      "note": "not an HBM-bound kernel: the 6 centred Gram matrices (32 MB each) are streamed from L2 "
                              "(hit rate ~70 %), no unit is saturated (ncu: lts 20 %, fp64 17 %, DRAM 14 %); the bound is "
@@ -620,8 +645,10 @@ def main():
                 "roofline": roofline, "cpu_baseline": cpu,
                 "best_params": res["best_params"], "best_score": float(res["best_score"])}
         if strong:
-            line["strong_scaling"] = getattr(sglm_dist, "last_timeline", None)
-        print(json.dumps(line))
+            line["strong_scaling"] = {"device_resident_step": device_timeline,
+                                      "e2e_step_from_host_arrays": getattr(sglm_dist, "last_timeline", None),
+                                      "unit": "ms per stage on rank 0 (CUDA events), last step of each leg"}
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

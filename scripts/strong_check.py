@@ -34,6 +34,13 @@ if rank == 0:
     folds = synth_data.synth_folds(d.shape[0], 5, 31, group=1000)
     single = sglm_cv.cv_glm_mult_params(d, y, folds, "Gaussian", [dict(g) for g in grid], score_method="r2")
     del d, s
+    # the one-GPU grid on the LAZY design (statistics from the base signals' digit planes) must equal the grid on the
+    # built design; the strong-scaled grid below takes the lazy path on every rank
+    lazy = sglm_pp.timeshift_multiple(torch.from_numpy(X0).cuda(), shift_amt_list=shifts, device=True).dropna()
+    single_lazy = sglm_cv.cv_glm_mult_params(lazy, y, folds, "Gaussian", [dict(g) for g in grid], score_method="r2")
+    for a, b in zip(single_lazy["full_cv_results"], single["full_cv_results"]):
+        assert np.array_equal(a["cv_coefs"], b["cv_coefs"]) and np.array_equal(a["model"].coef_, b["model"].coef_)
+    print("one GPU: lazy design == built design, bit-identical coefficients", flush=True)
 for it in range(2):
     res = sglm_dist.cv_grid_strong(X0, shifts, y, folds, "Gaussian", [dict(g) for g in grid], score_method="r2")
     tl = sglm_dist.last_timeline
