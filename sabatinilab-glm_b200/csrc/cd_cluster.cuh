@@ -602,14 +602,20 @@ enet_cd_cluster_kernel(const double *const *__restrict__ prob_Q, const double *c
                             if (!__all_sync(0xffffffffu, ok)) { ok = false; __nanosleep(64); guard.tick(); } else ok = true;
                         } while (!ok);
                     }
-                    const unsigned la_d = s_addr(rdelta + (slot * M + m) * RS + lane);
+                    // groups of 8: the deltas of a record are stored row-major, [row][model], so that a panel thread fetches
+                    // the 8 deltas of a row with four 16-byte loads; a model that did not move then has to send its zeros
+                    // (there is no all-zero page to point at)
+                    constexpr bool ROWMAJOR = M >= 8;
+                    const bool send = ROWMAJOR || nz != 0u;
+                    const unsigned la_d = ROWMAJOR ? s_addr(rdelta + ((size_t)slot * RS + lane) * M + m)
+                                                   : s_addr(rdelta + (slot * M + m) * RS + lane);
                     const unsigned la_m = s_addr(rmask + slot * M + m);
                     const unsigned la_b = s_addr(fullb + slot);
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
                         const unsigned rb = map_to(la_b, k);
-                        if (lane == 0) mbar_remote_arrive_tx(rb, nz ? 33u * 8u : 8u);
-                        if (nz) st_async_b64(map_to(la_d, k), (unsigned long long)__double_as_longlong(delta_l), rb);
+                        if (lane == 0) mbar_remote_arrive_tx(rb, send ? 33u * 8u : 8u);
+                        if (send) st_async_b64(map_to(la_d, k), (unsigned long long)__double_as_longlong(delta_l), rb);
                         if (lane == 0) st_async_b64(map_to(la_m, k), (unsigned long long)nz, rb);
                     }
                 }
@@ -665,15 +671,17 @@ enet_cd_cluster_kernel(const double *const *__restrict__ prob_Q, const double *c
                         }
                         unsigned rem = um;
                         if constexpr (M >= 8) {
-                            // wide groups: the deltas stay in shared memory until the row they scale has arrived
-                            // (M * RG of them in registers next to M * CH accumulators would not fit)
+                            // wide groups: the deltas of a row ([row][model] in the record) are fetched with M / 2 16-byte
+                            // loads right before the row's FMAs (M * RG of them in registers next to M * CH accumulators
+                            // would not fit into the 128 registers of a 512-thread CTA)
+                            const double2 *drec = reinterpret_cast<const double2 *>(rdelta + (size_t)slot * RS * M);
                             while (rem) {
                                 double2 v[RG][CH];
                                 int ii[RG];
 #pragma unroll
                                 for (int g = 0; g < RG; ++g) {
                                     const bool has = rem != 0u;
-                                    const int i = has ? (__ffs(rem) - 1) : 32;
+                                    const int i = has ? (__ffs(rem) - 1) : 32;        // 32: a row of zero deltas
                                     rem &= rem - 1;
                                     ii[g] = i;
                                     const double2 *row = Q2 + (long long)(i & 31) * ld2 + c0;
@@ -682,16 +690,21 @@ enet_cd_cluster_kernel(const double *const *__restrict__ prob_Q, const double *c
                                         v[g][u] = okc[u] ? __ldg(row + u * NTB) : make_double2(0.0, 0.0);
                                 }
 #pragma unroll
-                                for (int g = 0; g < RG; ++g)
+                                for (int g = 0; g < RG; ++g) {
+                                    const double2 *dp = drec + ii[g] * (M / 2);
+                                    double2 dd[M / 2];
 #pragma unroll
-                                    for (int mm = 0; mm < M; ++mm) {
-                                        const double dd = dlm[mm][ii[g]];
+                                    for (int h = 0; h < M / 2; ++h) dd[h] = dp[h];
+#pragma unroll
+                                    for (int h = 0; h < M / 2; ++h)
 #pragma unroll
                                         for (int u = 0; u < CH; ++u) {
-                                            acc[mm][u].x = fma(dd, v[g][u].x, acc[mm][u].x);
-                                            acc[mm][u].y = fma(dd, v[g][u].y, acc[mm][u].y);
+                                            acc[2 * h][u].x = fma(dd[h].x, v[g][u].x, acc[2 * h][u].x);
+                                            acc[2 * h][u].y = fma(dd[h].x, v[g][u].y, acc[2 * h][u].y);
+                                            acc[2 * h + 1][u].x = fma(dd[h].y, v[g][u].x, acc[2 * h + 1][u].x);
+                                            acc[2 * h + 1][u].y = fma(dd[h].y, v[g][u].y, acc[2 * h + 1][u].y);
                                         }
-                                    }
+                                }
                             }
                         } else {
                         while (rem) {
