@@ -427,6 +427,12 @@ int sglm_chol_solve_batched_f64(const double *const *L_of, int64_t ldq, int32_t 
  *                         state_host: the solver state (device pointers and sizes) as sglm_pb_state_words()
  *                         64-bit words — see PbState in csrc/poisson_batch.cu; built by _engine.py.
  * H~ = X' diag(rw mu_ref) X of one reference model per fold comes from sglm_gram_tc_scaled_f64 (tcgen05). */
+/* Quadratic forms of MANY vectors: out[m] = v_m' A v_m with the vectors as the columns of Vt [n][ldb] (ldb % 64 == 0,
+ * columns >= n_models zero): one fp64 GEMM Y = A Vt (A read once per 64 vectors) + column dots in 16 fixed row chunks
+ * (deterministic).  Y [n][ldb] and part [16][n_models] are caller buffers.  The scores of a CV grid from the
+ * statistics (RSS(model, row set) = v' G[set] v; the reference: three prediction passes per fit, backend/sglm.py:305-312). */
+int sglm_quadform_gemm_f64(const double *A, int64_t lda, int32_t n, const double *Vt, int64_t ldb, int32_t n_models,
+                           double *Y, double *part, double *out, void *stream);
 size_t sglm_pb_gemm_tn_workspace_bytes(int64_t T, int32_t C, int64_t ldb);
 int sglm_pb_eta_f64(const double *X, int64_t ldx, int64_t T, int32_t C, const double *Wt, int64_t ldb, double *Eta,
                     void *stream);

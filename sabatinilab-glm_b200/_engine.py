@@ -942,12 +942,26 @@ def finalize(W, C, n_y, models):
     return b, V
 
 
+QUADFORM_GEMM_MIN = 128     # vectors from which v'Av goes through the fp64 GEMM (below: the row-streaming kernel)
+
+
 def quadform(A, V):
     """out[m] = V[m]' A V[m]."""
     M = V.shape[0]
     n = A.shape[0]
     if not M:
         return _empty((0,))
+    if M >= QUADFORM_GEMM_MIN:
+        # many vectors: one fp64 GEMM A V' (A streamed once per 64 vectors) + deterministic column dots
+        torch = nat.require_cuda()
+        ldb = _round_up(M, 64)
+        Vt = _zeros((n, ldb))
+        Vt[:, :M] = V[:, :n].t()
+        Y = _empty((n, ldb))
+        part = _empty((16, M))
+        out = _empty((M,))
+        call("sglm_quadform_gemm_f64", ptr(A), A.stride(0), n, ptr(Vt), ldb, M, ptr(Y), ptr(part), ptr(out), stream_ptr())
+        return out
     # few models: split the rows of A over several CTAs per model group so that every SM streams a part
     groups = (M + 7) // 8
     splits = max(1, min(16, (2 * 148) // groups))

@@ -81,7 +81,7 @@ extern "C" int sglm_enet_cd_cluster_f64(const double *const *prob_Q, const doubl
     cdc::Args a{prob_Q, prob_q, prob_diag, prob_yy, (long long)ldq, C, prob_of_group, model_of_slot, l1_reg, l2_reg,
                 tol, max_iter, n_groups, warm_start, do_screening, W, (long long)ldw, info,
                 (const CUtensorMap *)prob_tmap, (cudaStream_t)stream, 0, group_stats};
-    if (const char *v = getenv("SGLM_CDC_VARIANT")) a.variant = atoi(v);      // tuning switch
+    if (const char *v = tuning_env("SGLM_CDC_VARIANT")) a.variant = atoi(v);      // tuning switch
     if (group_size == 1) return cdc::launch_m1(a, cluster_size);
     if (group_size == 2) return cdc::launch_m2(a, cluster_size);
     if (group_size == 8) return cdc::launch_m8(a, cluster_size);

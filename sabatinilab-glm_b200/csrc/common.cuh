@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -57,6 +58,13 @@ __device__ __forceinline__ double cd_soft_select(double r, double l1, double dpo
         "selp.f64 %0, %4, %0, p;\n\t}"
         : "=&d"(out) : "d"(r), "d"(l1), "d"(-l1), "d"(dpos), "d"(dneg), "d"(other));
     return out;
+}
+
+// Measurement switches (kernel shape variants, A/B forms) are honoured only when the process was started with
+// SGLM_TUNING=1 — read once; a production call never consults the environment.
+inline const char *tuning_env(const char *name) {
+    static const bool on = [] { const char *v = getenv("SGLM_TUNING"); return v && v[0] == '1'; }();
+    return on ? getenv(name) : nullptr;
 }
 
 __device__ __forceinline__ unsigned long long global_timer_ns() {

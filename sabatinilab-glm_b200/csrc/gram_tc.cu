@@ -778,7 +778,7 @@ static int gram_tc_analyze(const double *X, int64_t ldx, const double *Y, int64_
     }
     tc_exponent_kernel<<<ceil_div(n_aug, 256), 256, 0, st>>>((const unsigned long long *)colmax_scratch, n_aug, max_planes, colE, colS, flag);
     SGLM_LAUNCH_OK("tc_exponent_kernel");
-    if (T > 0 && max_planes == TC_SMAX && getenv("SGLM_TC_DIGIT_PASS")) {
+    if (T > 0 && max_planes == TC_SMAX && tuning_env("SGLM_TC_DIGIT_PASS")) {
         // validation switch: the digit-by-digit second pass (atomicMax on colS) must not raise any count
         tc_digits_kernel<<<grid, 256, 0, st>>>(X, ldx, Y, ldy, C, n_y, T, rs, colE, colS);
         SGLM_LAUNCH_OK("tc_digits_kernel");

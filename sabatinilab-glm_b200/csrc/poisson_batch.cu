@@ -402,6 +402,51 @@ extern "C" int sglm_pb_eta_f64(const double *X, int64_t ldx, int64_t T, int32_t 
     return SGLM_OK;
 }
 
+// ------------------------------------------------------------------ quadratic forms of many vectors: v_m' A v_m
+// out[m] = sum_i Vt[i][m] (A Vt)[i][m]: one fp64 GEMM (A is read once per 64 vectors instead of once per 8 as in
+// quadform_kernel) followed by column dots in fixed row chunks (deterministic).  Scores of a CV grid from the
+// statistics: RSS(model, row set) = v' G[set] v (backend/sglm.py:305-312 computes them by three prediction passes).
+constexpr int QG_PARTS = 16;
+__global__ void __launch_bounds__(128)
+coldot_kernel(const double *__restrict__ Vt, const double *__restrict__ Y, long long n, long long ldb, int n_models,
+              double *__restrict__ part) {
+    const int m = blockIdx.x * 128 + threadIdx.x;
+    if (m >= n_models) return;
+    const long long per = (n + QG_PARTS - 1) / QG_PARTS;
+    const long long i0 = (long long)blockIdx.y * per, i1 = min(n, i0 + per);
+    double acc = 0.0;
+    for (long long i = i0; i < i1; ++i) acc = fma(Vt[i * ldb + m], Y[i * ldb + m], acc);
+    part[(long long)blockIdx.y * n_models + m] = acc;
+}
+__global__ void __launch_bounds__(128)
+coldot_finish_kernel(const double *__restrict__ part, int n_models, double *__restrict__ out) {
+    const int m = blockIdx.x * 128 + threadIdx.x;
+    if (m >= n_models) return;
+    double s = 0.0;
+    for (int p = 0; p < QG_PARTS; ++p) s += part[(long long)p * n_models + m];
+    out[m] = s;
+}
+
+// Vt [n][ldb]: the vectors as COLUMNS (ldb % 64 == 0, columns >= n_models zero); work: 2 * n * ldb doubles is not needed —
+// Y [n][ldb] and part [16][n_models] are caller buffers.
+extern "C" int sglm_quadform_gemm_f64(const double *A, int64_t lda, int32_t n, const double *Vt, int64_t ldb,
+                                      int32_t n_models, double *Y, double *part, double *out, void *stream) {
+    SGLM_CHECK_ARG(n > 0 && lda >= n && n_models > 0 && ldb >= n_models && ldb % 64 == 0, SGLM_E_SHAPE, "quadform_gemm: bad shape");
+    SGLM_CHECK_ARG(A && Vt && Y && part && out, SGLM_E_INVALID_ARG, "quadform_gemm: null pointer");
+    SGLM_CHECK_ARG(((uintptr_t)Vt & 15) == 0 && ((uintptr_t)Y & 15) == 0, SGLM_E_ALIGN, "quadform_gemm: 16-byte alignment");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((unsigned)ceil_div<long long>(n, PB_BM), (unsigned)(ldb / PB_BN));
+    SGLM_CUDA_OK(cudaFuncSetAttribute(pb_gemm_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PB_GEMM_SMEM));
+    pb_gemm_nn_kernel<<<grid, PB_THREADS, PB_GEMM_SMEM, st>>>(A, lda, n, n, Vt, ldb, Y, ldb);
+    SGLM_LAUNCH_OK("pb_gemm_nn_kernel(quadform)");
+    dim3 dgrid((unsigned)ceil_div(n_models, 128), QG_PARTS);
+    coldot_kernel<<<dgrid, 128, 0, st>>>(Vt, Y, n, ldb, n_models, part);
+    SGLM_LAUNCH_OK("coldot_kernel");
+    coldot_finish_kernel<<<ceil_div(n_models, 128), 128, 0, st>>>(part, n_models, out);
+    SGLM_LAUNCH_OK("coldot_finish_kernel");
+    return SGLM_OK;
+}
+
 // Gw [C][ldb] = X' R   (R [T][ldb]); deterministic: fixed T chunks of 8192 rows, partials added in order
 extern "C" int sglm_pb_xt_r_f64(const double *X, int64_t ldx, int64_t T, int32_t C, const double *R, int64_t ldb,
                                 double *Gw, void *workspace, size_t workspace_bytes, void *stream) {

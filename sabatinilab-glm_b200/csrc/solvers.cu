@@ -1035,7 +1035,7 @@ extern "C" int sglm_enet_cd_gram_f64(const double *const *prob_Q, const double *
     } while (0)
     // (panel warps, 16-byte chunks per thread, rows per load group, min CTAs per SM): chosen so that
     // several models are resident per SM (profiles/r1_cd_variants.txt); SGLM_CD_VARIANT is a tuning switch
-    const char *var = getenv("SGLM_CD_VARIANT");
+    const char *var = tuning_env("SGLM_CD_VARIANT");
     const int variant = var ? atoi(var) : 0;
     if (C <= 256) CD_LAUNCH(1, 4, 4, 8);
     else if (C <= 512) CD_LAUNCH(2, 4, 4, 6);
@@ -1072,7 +1072,7 @@ extern "C" int sglm_ridge_solve_f64(const double *Qc, int64_t ldq, const double 
     SGLM_CHECK_ARG(Qc && qc && alpha && W && status && work, SGLM_E_INVALID_ARG, "ridge_solve: null pointer");
     SGLM_CHECK_ARG(work_bytes >= sglm_ridge_workspace_bytes(C, ldq, n_alpha), SGLM_E_WORKSPACE,
                    "ridge_solve: workspace too small");
-    const char *form = getenv("SGLM_CHOLESKY");             // "right": the first right-looking kernel (A/B switch)
+    const char *form = tuning_env("SGLM_CHOLESKY");             // "right": the first right-looking kernel (A/B switch)
     if (form && form[0] == 'r') {
         const size_t smem = (size_t)(RC_NB * 33 + 2 * 64 * 33 + C) * sizeof(double);
         SGLM_CHECK_ARG(smem <= 227 * 1024, SGLM_E_UNSUPPORTED, "ridge_solve: C=%d too large for shared memory", C);

@@ -33,6 +33,7 @@ def run(plan, sel, models):
     return dt, info[h, 4], info[h, 5], info[:, 3].sum()
 for item in os.environ.get("DIAG_PLANS", "4x2@0.3,0x0").split(";"):
     plan, _, var = item.partition("#")
+    os.environ["SGLM_TUNING"] = "1"
     os.environ["SGLM_CDC_VARIANT"] = var or "0"
     for every in [int(v) for v in os.environ.get('DIAG_EVERY', '1,2,8').split(',')]:
         models = ms[::every] if every > 1 else ms

@@ -16,6 +16,7 @@ X[:, 144] = rng.standard_normal(T) * 1e12
 y = rng.standard_normal((T, 1))
 Xd, Yd = torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda()
 _, s1 = eng.suffstats_tc(Xd, Yd, [None])
+os.environ["SGLM_TUNING"] = "1"
 os.environ["SGLM_TC_DIGIT_PASS"] = "1"
 _, s2 = eng.suffstats_tc(Xd, Yd, [None])
 print("one-pass == digit pass:", np.array_equal(s1, s2), "planes", s1.sum(), s2.sum())

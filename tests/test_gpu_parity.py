@@ -864,3 +864,27 @@ def test_fit_set_in_place_semantics_from_threads():
         assert abs(tr[k] - ref.r2_score(X[a], y[a])) < 1e-6 and abs(te[k] - ref.r2_score(X[b], y[b])) < 1e-6
     pooled = sglm.calc_R2(np.concatenate(resids), np.concatenate(mean_resids))
     assert -1.0 < pooled < 1.0
+
+
+def test_quadform_gemm_path_equals_row_streaming_kernel():
+    """v' A v of many vectors through the fp64 GEMM (sglm_quadform_gemm_f64) against the row-streaming kernel and numpy:
+    ragged sizes (n not a multiple of the tiles, M not a multiple of 64), padded leading dimensions."""
+    rng = np.random.default_rng(11)
+    for n, M in [(203, 130), (1221, 300), (64, 128)]:
+        B = rng.standard_normal((n, n))
+        A = torch.from_numpy(B @ B.T).cuda()
+        Apad = torch.zeros((n, n + 5), dtype=torch.float64, device="cuda")
+        Apad[:, :n] = A
+        V = torch.from_numpy(rng.standard_normal((M, n + (n & 1)))).cuda()
+        want = np.einsum("mi,ij,mj->m", V[:, :n].cpu().numpy(), A.cpu().numpy(), V[:, :n].cpu().numpy())
+        old = eng.QUADFORM_GEMM_MIN
+        try:
+            eng.QUADFORM_GEMM_MIN = 1 << 30
+            q_rows = eng.quadform(Apad[:, :n], V).cpu().numpy()
+            eng.QUADFORM_GEMM_MIN = 1
+            q_gemm = eng.quadform(Apad[:, :n], V).cpu().numpy()
+        finally:
+            eng.QUADFORM_GEMM_MIN = old
+        scale = np.abs(want).max()
+        assert np.max(np.abs(q_rows - want)) < 1e-12 * scale
+        assert np.max(np.abs(q_gemm - want)) < 1e-12 * scale
