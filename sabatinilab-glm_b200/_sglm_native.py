@@ -158,9 +158,11 @@ def ptr(t):
 
 
 # kernels launched per ABI call (for the launch count bench.py reports)
-_KERNELS_PER_CALL = {"sglm_suffstats_f64": 3, "sglm_gram_tc_analyze_f64": 3, "sglm_gram_tc_f64": 3, "sglm_gram_tc_cells_f64": 4, "sglm_gram_tc_lag_cells_f64": 6, "sglm_quadform_gemm_f64": 3, "sglm_gram_tc_cells_partial_f64": 3, "sglm_gram_tc_scaled_f64": 3, "sglm_gram_tc_analyze_scaled_f64": 2, "sglm_xt_vec_f64": 2, "sglm_score_f64": 2, "sglm_poisson_irls_prepare_f64": 2,
-                     "sglm_timeshift_f64": 2, "sglm_pb_xt_r_f64": 2, "sglm_pb_epilogue_f64": 2, "sglm_pb_step_f64": 3,
-                     "sglm_lag_valid_rows": 3, "sglm_col_moments_f64": 4, "sglm_mask_compact_rows": 3}
+_KERNELS_PER_CALL = {"sglm_suffstats_f64": 3, "sglm_gram_tc_analyze_f64": 2, "sglm_gram_tc_f64": 4, "sglm_gram_tc_cells_f64": 5,
+                     "sglm_gram_tc_lag_cells_f64": 7, "sglm_gram_tc_cells_partial_f64": 4, "sglm_gram_tc_scaled_f64": 4,
+                     "sglm_gram_tc_analyze_scaled_f64": 2, "sglm_quadform_gemm_f64": 3, "sglm_xt_vec_f64": 2, "sglm_score_f64": 2,
+                     "sglm_poisson_irls_prepare_f64": 2, "sglm_timeshift_f64": 2, "sglm_pb_xt_r_f64": 2, "sglm_pb_epilogue_f64": 2,
+                     "sglm_pb_step_f64": 3, "sglm_lag_valid_rows": 3, "sglm_col_moments_f64": 4, "sglm_mask_compact_rows": 3}
 _timing = None         # when enabled: list of (name, start_event, end_event) on the current stream
 
 

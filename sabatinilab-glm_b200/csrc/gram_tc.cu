@@ -202,40 +202,52 @@ tc_slice_kernel(const double *__restrict__ X, long long ldx, const double *__res
 // At[(plane k of column c)][pos] = Bt[(plane k of p_c)][rows[pos] + off_c] is a byte gather (reads hit L1 / L2: the L
 // shifts of a signal read the same bytes; HBM traffic = the write of At).  map[r] = (row of Bt, off) of At row r,
 // (-1, .) for rows that are not lag columns (response / ones planes, padding between levels).
-constexpr int TC_EXP_ROWS = 512;     // At rows per CTA (blockIdx.y)
+constexpr int TC_EXP_ROWS = 256;     // At rows per CTA (blockIdx.y)
+constexpr int TC_EXP_POS = 512;      // positions per CTA: 32 chunks of 16 positions (one 16-byte store each)
 __global__ void __launch_bounds__(256)
 tc_expand_kernel(const int8_t *__restrict__ Bt, long long ld_bt, const long long *__restrict__ rows, long long n_pos,
                  const int2 *__restrict__ map, int n_at_rows, int8_t *__restrict__ At, long long ld_at) {
-    __shared__ long long srow[128];
+    __shared__ long long srow[TC_EXP_POS];
     const int tid = threadIdx.x;
-    const long long p0 = (long long)blockIdx.x * 128;
-    if (tid < 128) srow[tid] = (p0 + tid < n_pos) ? rows[p0 + tid] : -1;
+    const long long p0 = (long long)blockIdx.x * TC_EXP_POS;
+    for (int i = tid; i < TC_EXP_POS; i += 256) srow[i] = (p0 + i < n_pos) ? rows[p0 + i] : -1;
     __syncthreads();
     const int pq = tid & 31, rl = tid >> 5;
-    const long long p = p0 + 4 * pq;
-    if (p >= n_pos) return;
-    const long long r0 = srow[4 * pq], r1 = srow[4 * pq + 1], r2 = srow[4 * pq + 2], r3 = srow[4 * pq + 3];
-    const bool contig = r0 >= 0 && r1 == r0 + 1 && r2 == r0 + 2 && r3 == r0 + 3;
+    const long long p = p0 + 16 * pq;
+    if (p >= n_pos) return;                         // n_pos is a multiple of 128: whole chunks only
+    const long long r0 = srow[16 * pq], r15 = srow[16 * pq + 15];
+    // sorted, duplicate-free row lists: 16 positions are 16 consecutive rows iff last - first == 15 (padding is -1)
+    const bool contig = r0 >= 0 && r15 == r0 + 15;
     const int r_end = min(n_at_rows, (int)(blockIdx.y + 1) * TC_EXP_ROWS);
     for (int r = blockIdx.y * TC_EXP_ROWS + rl; r < r_end; r += 8) {
         const int2 m = map[r];
         if (m.x < 0) continue;
         const int8_t *src = Bt + (long long)m.x * ld_bt + m.y;
-        unsigned pack;
+        uint4 out;
         if (contig) {
-            // four consecutive bytes at an arbitrary byte offset: two aligned words and a funnel shift
+            // 16 consecutive bytes at an arbitrary byte offset: five aligned words and four funnel shifts
             const unsigned long long a = (unsigned long long)(src + r0);
             const unsigned *w = reinterpret_cast<const unsigned *>(a & ~3ull);
             const unsigned sh = (unsigned)(a & 3ull) * 8u;
-            const unsigned lo = __ldg(w);
-            const unsigned hi = sh ? __ldg(w + 1) : 0u;
-            pack = __funnelshift_r(lo, hi, sh);
+            const unsigned w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
+            const unsigned w4 = sh ? __ldg(w + 4) : 0u;
+            out = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                             __funnelshift_r(w3, w4, sh));
         } else {
-            const unsigned b0 = r0 >= 0 ? (unsigned char)__ldg(src + r0) : 0u, b1 = r1 >= 0 ? (unsigned char)__ldg(src + r1) : 0u;
-            const unsigned b2 = r2 >= 0 ? (unsigned char)__ldg(src + r2) : 0u, b3 = r3 >= 0 ? (unsigned char)__ldg(src + r3) : 0u;
-            pack = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+            unsigned q[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                unsigned v = 0u;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const long long rr = srow[16 * pq + 4 * j + b];
+                    if (rr >= 0) v |= (unsigned)(unsigned char)__ldg(src + rr) << (8 * b);
+                }
+                q[j] = v;
+            }
+            out = make_uint4(q[0], q[1], q[2], q[3]);
         }
-        *reinterpret_cast<unsigned *>(At + (long long)r * ld_at + p) = pack;
+        *reinterpret_cast<uint4 *>(At + (long long)r * ld_at + p) = out;
     }
 }
 
@@ -540,12 +552,26 @@ tc_gram_i8_check_kernel(const int8_t *__restrict__ At, long long ld_at, const in
 // disjoint CELLS of the partition they induce and the Gram of each set is the sum of its cells' Grams.
 constexpr int TC_SUM_OUT = 8;      // output sets accumulated per pass over the cells
 constexpr int TC_SUM_CELLS = 256;  // cells whose membership masks are staged in shared memory
+// Only the output tiles the GEMM computes (level pairs k <= l, upper triangle inside a level: 193 of 484 tiles at c3) are
+// zeroed, summed and later read by the recombination; the rest of the S x S planes is never touched.
 __global__ void __launch_bounds__(256)
-tc_cell_sum_kernel(const long long *__restrict__ SG, long long n_elem, int n_cells, const int *__restrict__ member,
-                   int n_out, long long *__restrict__ SGout) {
-    // every cell element is read once per group of TC_SUM_OUT output sets and added to the sets it belongs to;
-    // membership of a cell = one bit mask per group (shared memory), two elements per thread, cells unrolled by 4
+tc_zero_tiles_kernel(long long *__restrict__ SG, long long S, const int2 *__restrict__ tiles) {
+    const int2 tile = tiles[blockIdx.x];
+    long long *base = SG + (long long)blockIdx.y * S * S + (long long)tile.x * TC_BM * S + (long long)tile.y * TC_BN;
+    for (int e = threadIdx.x; e < TC_BM * TC_BN / 2; e += 256) {
+        const int r = e / (TC_BN / 2), c2 = e % (TC_BN / 2);
+        reinterpret_cast<longlong2 *>(base + (long long)r * S)[c2] = make_longlong2(0, 0);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+tc_cell_sum_kernel(const long long *__restrict__ SG, long long S, const int2 *__restrict__ tiles, int n_tiles, int n_cells,
+                   const int *__restrict__ member, int n_out, long long *__restrict__ SGout) {
+    // every element of a computed tile is read once per group of TC_SUM_OUT output sets and added to the sets it belongs
+    // to; membership of a cell = one bit mask per group (shared memory), two elements per thread, cells unrolled by 4
     __shared__ unsigned smask[TC_SUM_CELLS];
+    const long long n_elem = S * S;
+    const long long n_pairs = (long long)n_tiles * (TC_BM * TC_BN / 2);
     for (int o0 = 0; o0 < n_out; o0 += TC_SUM_OUT) {
         __syncthreads();
         for (int c = threadIdx.x; c < n_cells && c < TC_SUM_CELLS; c += 256) {
@@ -555,8 +581,11 @@ tc_cell_sum_kernel(const long long *__restrict__ SG, long long n_elem, int n_cel
             smask[c] = m;
         }
         __syncthreads();
-        for (long long e = ((long long)blockIdx.x * 256 + threadIdx.x) * 2; e < n_elem; e += (long long)gridDim.x * 512) {
-            const bool two = e + 1 < n_elem;
+        for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < n_pairs; t += (long long)gridDim.x * 256) {
+            const int2 tile = tiles[t / (TC_BM * TC_BN / 2)];
+            const int w = (int)(t % (TC_BM * TC_BN / 2));
+            const long long e = ((long long)tile.x * TC_BM + w / (TC_BN / 2)) * S + (long long)tile.y * TC_BN + 2 * (w % (TC_BN / 2));
+            const bool two = true;
             long long a0[TC_SUM_OUT], a1[TC_SUM_OUT];
 #pragma unroll
             for (int k = 0; k < TC_SUM_OUT; ++k) { a0[k] = 0; a1[k] = 0; }
@@ -1029,7 +1058,6 @@ static int gram_tc_run(const double *X, int64_t ldx, const double *Y, int64_t ld
         if (p.S > covered) SGLM_CUDA_OK(cudaMemsetAsync(At + covered * p.n_pos, 0, (size_t)(p.S - covered) * p.n_pos, st));
     }
     if (stage != 2) {
-        SGLM_CUDA_OK(cudaMemsetAsync(SG, 0, (size_t)p.n_sets * p.S * p.S * sizeof(long long), st));
         SGLM_CUDA_OK(cudaMemcpyAsync(d_plane, p.plane_row.data(), p.plane_row.size() * sizeof(int), cudaMemcpyHostToDevice, st));
         SGLM_CUDA_OK(cudaMemcpyAsync(d_tiles, p.tiles.data(), p.tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
         SGLM_CUDA_OK(cudaMemcpyAsync(d_segs, p.segs.data(), p.segs.size() * sizeof(TcSeg), cudaMemcpyHostToDevice, st));
@@ -1084,7 +1112,7 @@ static int gram_tc_run(const double *X, int64_t ldx, const double *Y, int64_t ld
         tc_slice_kernel<<<bgrid, 256, 0, st>>>(lag->base, lag->ldb, nullptr, 0, lag->P, 0, nullptr, nullptr, LL.ld_bt, lag->baseE,
                                                lag->baseS, (const int *)(ws + LL.off_bplane), Bt, LL.ld_bt, lag->n_u);
         SGLM_LAUNCH_OK("tc_slice_kernel(base)");
-        dim3 egrid((unsigned)(p.n_pos / 128), (unsigned)ceil_div((int)p.S, TC_EXP_ROWS));
+        dim3 egrid((unsigned)ceil_div<long long>(p.n_pos, TC_EXP_POS), (unsigned)ceil_div((int)p.S, TC_EXP_ROWS));
         tc_expand_kernel<<<egrid, 256, 0, st>>>(Bt, LL.ld_bt, (const long long *)rows, p.n_pos, (const int2 *)(ws + LL.off_map),
                                                 (int)p.S, At, p.n_pos);
         SGLM_LAUNCH_OK("tc_expand_kernel");
@@ -1101,6 +1129,10 @@ static int gram_tc_run(const double *X, int64_t ldx, const double *Y, int64_t ld
     }
 
     const int n_tiles = (int)p.tiles.size();
+    if (n_tiles > 0) {
+        tc_zero_tiles_kernel<<<dim3((unsigned)n_tiles, (unsigned)p.n_sets), 256, 0, st>>>(SG, p.S, d_tiles);
+        SGLM_LAUNCH_OK("tc_zero_tiles_kernel");
+    }
     if (use_check_gemm) {
         tc_gram_i8_check_kernel<<<n_tiles, 256, 0, st>>>(At, p.n_pos, d_tiles, d_segs, (int)p.segs.size(), SG, p.S);
         SGLM_LAUNCH_OK("tc_gram_i8_check_kernel");
@@ -1125,7 +1157,7 @@ static int gram_tc_run(const double *X, int64_t ldx, const double *Y, int64_t ld
     const long long *SGfin = SG;
     int n_fin = n_sets;
     if (n_out > 0) {
-        tc_cell_sum_kernel<<<sm_count() * 8, 256, 0, st>>>(SG, p.S * p.S, n_sets, d_member, n_out, SGout);
+        tc_cell_sum_kernel<<<sm_count() * 8, 256, 0, st>>>(SG, p.S, d_tiles, n_tiles, n_sets, d_member, n_out, SGout);
         SGLM_LAUNCH_OK("tc_cell_sum_kernel");
         SGfin = SGout;
         n_fin = n_out;
