@@ -40,6 +40,8 @@ constexpr int TC_STAGES = 3;
 constexpr int TC_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 constexpr int TC_MAX_KB_PER_SEG = 2048;   // 2048 * 128 rows * 2^12 < 2^31
 constexpr uint32_t TC_STAGE_BYTES = (TC_BM + TC_BN) * TC_BK;
+constexpr int TC_LEAD = 64;      // K blocks an item may run ahead of the slowest neighbouring item of its K part
+constexpr int TC_FAR = 1024;     // items further behind than this belong to another wave
 
 // ------------------------------------------------------------------ column scale and digit count
 __device__ __forceinline__ double z_value(const double *X, long long ldx, const double *Y, long long ldy,
@@ -286,6 +288,21 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tmap, 
         ::"r"(smem_u32(dst)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// multicast forms: the box lands at the same shared-memory offset of every CTA in `mask` and completes bytes on the mbarrier
+// at the same offset there; the commit arrives on the mbarrier at the same offset of every CTA in `mask`
+__device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *tmap, uint64_t *bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
@@ -326,7 +343,8 @@ struct TcSeg { int kb0, n_kb, set, first; };
 // square as TMEM allows: 512 operand rows per 65536 outputs.
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gram_i8_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restrict__ tiles, int n_tiles,
-                  int n_parts, const TcSeg *__restrict__ segs, int n_segs, long long *__restrict__ SG, long long S) {
+                  int n_parts, const TcSeg *__restrict__ segs, int n_segs, long long *__restrict__ SG, long long S,
+                  int *__restrict__ prog, const int2 *__restrict__ pairs, int n_pairs) {
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     uint8_t *base = (uint8_t *)(((uintptr_t)tc_smem + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = base;                                           // [STAGES][256][128]
@@ -336,10 +354,18 @@ tc_gram_i8_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restri
     uint32_t *tmem_slot = (uint32_t *)(tmem_empty + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // a 2-CTA cluster per (pair of neighbouring tiles of one tile row, K part): CTA `rank` computes tile pr.x / pr.y; both
+    // need the same A strip, each loads half of it and multicasts it to the other (half the A bytes through each SM's L2
+    // port: the kernel is bound by the L2 -> SM ingest per SM, ~55 GB/s, not by DRAM or the tensor pipe)
     const int item = blockIdx.x;
-    const int2 tile = tiles[item % n_tiles];
-    const int part = item / n_tiles;
+    const int rank = item & 1;
+    const int2 pr = pairs[(item >> 1) % n_pairs];
+    const int part = (item >> 1) / n_pairs;
+    const bool paired = pr.y >= 0;
+    const int my_tile = rank == 0 ? pr.x : pr.y;
+    const int2 tile = tiles[my_tile >= 0 ? my_tile : pr.x];
     const int m0 = tile.x * TC_BM, n0 = tile.y * TC_BN;
+    (void)n_tiles;
     // This item's share of the K space: part p owns a CONTIGUOUS range of the concatenated K blocks of all
     // segments (so a tile is drained once per row set plus once per part boundary, however many row sets
     // there are).  seg_range gives its K blocks [lo, hi) inside segment sgi; `before` = K blocks of the
@@ -354,7 +380,8 @@ tc_gram_i8_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restri
     };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        // a stage is free when the MMAs of BOTH CTAs have read it (the peer multicasts into it)
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, paired ? 2 : 1); }
         mbar_init(tmem_full, 1);
         mbar_init(tmem_empty, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -365,32 +392,72 @@ tc_gram_i8_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restri
     }
     tc_fence_before();
     __syncthreads();
+    tc_cluster_sync();               // the peer's barriers exist before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_acc = *tmem_slot;
+    const uint16_t mc_mask = paired ? (uint16_t)3 : (uint16_t)(1u << rank);
 
-    if (warp == 0) {
-        // ===== TMA producer (one elected lane)
-        if (lane == 0) {
-            int it = 0;
-            long long before = 0;
-            for (int sgi = 0; sgi < n_segs; ++sgi) {
-                int lo, hi;
-                seg_range(segs[sgi], before, lo, hi);
-                before += segs[sgi].n_kb;
-                for (int kb = lo; kb < hi; ++kb, ++it) {
+    if (my_tile < 0) {
+        // the idle half of a cluster whose tile has no neighbour
+        if (prog != nullptr && threadIdx.x == 0)
+            asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(prog + item), "r"(0x7fffffff) : "memory");
+    } else if (warp == 0) {
+        // ===== TMA producer (one elected lane issues the loads; the whole warp keeps the K schedule in step)
+        // Optional K lock-step (prog != nullptr; measurement switch SGLM_TC_LOCKSTEP): the work items of one K part read the
+        // same operand strips; while they walk K together every strip byte is fetched from DRAM once and served from L2 to
+        // the ~13 CTAs that need it, left alone they drift apart by more than the ~175 K blocks L2 can hold and the strips
+        // are re-fetched ~10x (ncu: 97 GB of DRAM reads for 9.6 GB of digit planes, L2 hit 51 %).  Every 32 K blocks an item
+        // publishes its position and does not run more than TC_LEAD K blocks ahead of the slowest item of its part in its
+        // neighbourhood (items further than TC_FAR behind belong to a later wave; finished / not yet started items are
+        // ignored) — the slowest item never waits, so the scheme cannot deadlock.  It cuts the DRAM reads 4x and does NOT
+        // make the kernel faster (it is bound by the L2 -> SM ingest per SM), so it is off by default.
+        int it = 0;
+        long long before = 0;
+        for (int sgi = 0; sgi < n_segs; ++sgi) {
+            int lo, hi;
+            seg_range(segs[sgi], before, lo, hi);
+            before += segs[sgi].n_kb;
+            for (int kb = lo; kb < hi; ++kb, ++it) {
+                if (prog != nullptr && (it & 31) == 0) {
+                    __syncwarp();
+                    if (lane == 0) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(prog + item), "r"(it) : "memory");
+                    const int *grp = prog + (long long)part * 2 * n_pairs;
+                    const long long t_start = clock64();
+                    while (true) {
+                        int behind = 0;
+                        for (int j = lane; j < 2 * n_pairs; j += 32) {
+                            int v;
+                            asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(grp + j) : "memory");
+                            const int d = it - v;
+                            if (v >= 0 && d > TC_LEAD && d <= TC_FAR) behind = 1;
+                        }
+                        if (!__any_sync(0xffffffffu, behind)) break;
+                        __nanosleep(500);
+                        if (clock64() - t_start > 4000000000LL) { asm volatile("trap;"); }
+                    }
+                }
+                if (lane == 0) {
                     const int st = it % TC_STAGES;
                     const uint32_t ph = (it / TC_STAGES) & 1;
                     mbar_wait(empty + st, ph ^ 1);
                     mbar_expect_tx(full + st, TC_STAGE_BYTES);
                     const int kc = kb * TC_BK;
                     uint8_t *a = sA + st * TC_BM * TC_BK, *bq = sB + st * TC_BN * TC_BK;
-                    tma_load_2d(a, &tmap, full + st, kc, m0);
-                    tma_load_2d(a + 128 * TC_BK, &tmap, full + st, kc, m0 + 128);
+                    if (paired) {
+                        // my half of the shared A strip, to both CTAs; the other half arrives from the peer
+                        tma_load_2d_mc(a + rank * 128 * TC_BK, &tmap, full + st, kc, m0 + 128 * rank, mc_mask);
+                    } else {
+                        tma_load_2d(a, &tmap, full + st, kc, m0);
+                        tma_load_2d(a + 128 * TC_BK, &tmap, full + st, kc, m0 + 128);
+                    }
                     tma_load_2d(bq, &tmap, full + st, kc, n0);
                     tma_load_2d(bq + 128 * TC_BK, &tmap, full + st, kc, n0 + 128);
                 }
             }
         }
+        __syncwarp();
+        if (prog != nullptr && lane == 0)
+            asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(prog + item), "r"(0x7fffffff) : "memory");
     } else if (warp == 1) {
         // ===== MMA issuer (one elected lane)
         if (lane == 0) {
@@ -417,7 +484,8 @@ tc_gram_i8_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restri
                         tc_mma_i8(tmem_acc, da0 + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, accflag);
                         tc_mma_i8(tmem_acc + 256u, da1 + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, accflag);
                     }
-                    tc_commit(empty + st);                         // frees the stage when these MMAs retire
+                    if (paired) tc_commit_mc(empty + st, mc_mask);  // frees the stage in BOTH CTAs when these MMAs retire
+                    else tc_commit(empty + st);
                 }
                 tc_commit(tmem_full);                              // accumulators of this segment complete
                 ++drained;
@@ -470,6 +538,7 @@ tc_gram_i8_kernel(const __grid_constant__ CUtensorMap tmap, const int2 *__restri
     }
     tc_fence_before();
     __syncthreads();
+    tc_cluster_sync();               // no CTA leaves while its peer may still multicast into it or arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(512));
@@ -679,6 +748,7 @@ struct TcPlan {
     std::vector<int> plane_row;         // [n_aug * TC_SMAX]
     std::vector<int> level_off, level_cnt;
     std::vector<int2> tiles;
+    std::vector<int2> pairs;            // (tile, right-hand neighbour in the same tile row | -1): one 2-CTA cluster each
     int n_parts;                        // K parts per tile (work items = tiles * n_parts)
     std::vector<TcSeg> segs;
     std::vector<long long> set_pos0;    // first position of each set
@@ -711,10 +781,21 @@ static void tc_make_plan(int n_aug, const int *colS, int n_sets, const long long
                     p.tiles.push_back(make_int2(mt, nt));
                 }
         }
+    // pairs of neighbouring tiles of one tile row share their A strip: a 2-CTA cluster loads it once (TMA multicast)
+    p.pairs.clear();
+    for (size_t i = 0; i < p.tiles.size();) {
+        if (i + 1 < p.tiles.size() && p.tiles[i + 1].x == p.tiles[i].x && p.tiles[i + 1].y == p.tiles[i].y + 1) {
+            p.pairs.push_back(make_int2((int)i, (int)i + 1));
+            i += 2;
+        } else {
+            p.pairs.push_back(make_int2((int)i, -1));
+            i += 1;
+        }
+    }
     // K parts: fill the SMs evenly (>= 3 waves when the K extent allows it)
     {
         const int sms = sm_count();
-        const int nt = std::max<int>(1, (int)p.tiles.size());
+        const int nt = std::max<int>(1, 2 * (int)p.pairs.size());
         long long total_kb = 0;
         for (int s = 0; s < n_sets; ++s) total_kb += (set_rows[s] + TC_BK - 1) / TC_BK;
         int best = 1;
@@ -727,6 +808,7 @@ static void tc_make_plan(int n_aug, const int *colS, int n_sets, const long long
             if (score > best_eff) { best_eff = score; best = parts; }
         }
         p.n_parts = best;
+        if (const char *v = tuning_env("SGLM_TC_PARTS")) p.n_parts = std::max(1, std::min(16, atoi(v)));      // measurement switch
     }
     // K segments: each set's rows padded to 128, cut into pieces that cannot overflow int32
     p.segs.clear(); p.set_pos0.assign(n_sets, 0);
@@ -749,7 +831,7 @@ static void tc_make_plan(int n_aug, const int *colS, int n_sets, const long long
 
 static inline size_t tc_align(size_t x) { return (x + 1023) & ~(size_t)1023; }
 
-struct TcLayout { size_t off_at, off_sg, off_sgout, off_member, off_plane, off_tiles, off_segs, total; };
+struct TcLayout { size_t off_at, off_sg, off_sgout, off_member, off_plane, off_tiles, off_segs, off_prog, off_pairs, total; };
 
 // n_out > 0: the plan's sets are cells and n_out row sets are summed from them (extra int64 Grams + the
 // membership table)
@@ -763,6 +845,8 @@ static TcLayout tc_layout(const TcPlan &p, int n_out = 0) {
     L.off_plane = o; o += tc_align(p.plane_row.size() * sizeof(int));
     L.off_tiles = o; o += tc_align(p.tiles.size() * sizeof(int2));
     L.off_segs = o; o += tc_align(p.segs.size() * sizeof(TcSeg));
+    L.off_prog = o; o += tc_align(2 * p.pairs.size() * (size_t)std::max(p.n_parts, 1) * sizeof(int));
+    L.off_pairs = o; o += tc_align(p.pairs.size() * sizeof(int2));
     L.total = o;
     return L;
 }
@@ -1060,6 +1144,7 @@ static int gram_tc_run(const double *X, int64_t ldx, const double *Y, int64_t ld
     if (stage != 2) {
         SGLM_CUDA_OK(cudaMemcpyAsync(d_plane, p.plane_row.data(), p.plane_row.size() * sizeof(int), cudaMemcpyHostToDevice, st));
         SGLM_CUDA_OK(cudaMemcpyAsync(d_tiles, p.tiles.data(), p.tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+        SGLM_CUDA_OK(cudaMemcpyAsync(ws + L.off_pairs, p.pairs.data(), p.pairs.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
         SGLM_CUDA_OK(cudaMemcpyAsync(d_segs, p.segs.data(), p.segs.size() * sizeof(TcSeg), cudaMemcpyHostToDevice, st));
     }
     long long *SGout = (long long *)(ws + L.off_sgout);
@@ -1150,8 +1235,26 @@ static int gram_tc_run(const double *X, int64_t ldx, const double *Y, int64_t ld
         SGLM_CHECK_ARG(r == CUDA_SUCCESS, SGLM_E_CUDA, "gram_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
         const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + 256;
         SGLM_CUDA_OK(cudaFuncSetAttribute(tc_gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc_gram_i8_kernel<<<n_tiles * p.n_parts, TC_THREADS, smem, st>>>(tmap, d_tiles, n_tiles, p.n_parts, d_segs,
-                                                                        (int)p.segs.size(), SG, p.S);
+        int *d_prog = (int *)(ws + L.off_prog);
+        // measured (profiles/r2_cd_experiments.txt section 12): the K lock-step cuts the DRAM reads 97 -> 25 GB (L2 hit 51 -> 79 %)
+        // but the kernel is bound by the L2 -> SM ingest per SM, not by DRAM; with the A strip multicast the throttling only
+        // costs time (stage 33.7 ms against 28.6 ms) — off unless asked for
+        const bool lockstep = tuning_env("SGLM_TC_LOCKSTEP") != nullptr;
+        const int n_pairs = (int)p.pairs.size();
+        if (lockstep) SGLM_CUDA_OK(cudaMemsetAsync(d_prog, 0xff, (size_t)2 * n_pairs * p.n_parts * sizeof(int), st));   // -1: not started
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * n_pairs * p.n_parts));
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        SGLM_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_gram_i8_kernel, tmap, (const int2 *)d_tiles, n_tiles, p.n_parts, (const TcSeg *)d_segs,
+                                        (int)p.segs.size(), SG, (long long)p.S, lockstep ? d_prog : (int *)nullptr,
+                                        (const int2 *)(ws + L.off_pairs), n_pairs));
         SGLM_LAUNCH_OK("tc_gram_i8_kernel");
     }
     const long long *SGfin = SG;
