@@ -220,3 +220,36 @@ def test_exporters_and_gen2_layout_without_gpu(tmp_path):
     for rel in ("models/sglm.py", "models/sglm_cv.py", "models/split_data.py", "models/eval.py", "models/train_model.py",
                 "features/sglm_pp.py", "features/setup_model_fit.py", "data/save_results.py"):
         assert os.path.exists(os.path.join(tree, rel)), rel
+
+
+def test_lag_recipe_window_and_offsets():
+    """Host logic of the never-built lag design (_engine.LagRecipe): the window of base rows every column reads, the per-column
+    offsets (design row t of column c = window row t + off[c]) and the cases that must fall back to building the design."""
+    import _engine as eng
+
+    class Base:                      # only .shape is consulted by window()
+        def __init__(self, T, P):
+            self.shape = (T, P)
+
+    T, P = 1000, 3
+    sh = np.array([0, -2, -1, 1, 3, 3], dtype=np.int32)          # out[t, c] = base[t - sh[c], src[c]]
+    src = np.array([0, 1, 2, 0, 1, 2], dtype=np.int32)
+    # rows kept by dropna: t - sh >= 0 and t - sh < T for every column -> [3, 998)
+    r = eng.LagRecipe(Base(T, P), src, sh, 3, 998, float("nan"))
+    assert r.shape == (995, 6)
+    u0, n_u, off = r.window()
+    assert u0 == 0 and n_u == 1000
+    # design row 0 is base row 3 - sh[c]
+    assert list(off) == [3, 5, 4, 2, 0, 0]
+    assert off.min() >= 0 and off.max() + r.shape[0] <= n_u
+    # an interior slice of rows (what one of several GPUs holds): the window moves with it
+    r2 = eng.LagRecipe(Base(T, P), src, sh, 400, 650, float("nan"))
+    u0, n_u, off = r2.window()
+    assert (u0, n_u) == (397, 255) and list(off) == [3, 5, 4, 2, 0, 0]
+    # columns that read outside the base signals (fill values would be needed): no window -> the design is built
+    assert eng.LagRecipe(Base(T, P), src, sh, 0, T, 0.0).window() is None
+    assert eng.LagRecipe(Base(T, P), src, sh, 2, 998, 0.0).window() is None
+    assert eng.LagRecipe(Base(T, P), src, sh, 3, 999, 0.0).window() is None
+    # empty designs
+    assert eng.LagRecipe(Base(T, P), src, sh, 5, 5, 0.0).window() is None
+    assert eng.LagRecipe(Base(T, P), src[:0], sh[:0], 0, T, 0.0).window() is None
