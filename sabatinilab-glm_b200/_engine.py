@@ -682,21 +682,34 @@ def _CD_DEFAULT_PLAN(C, n_models, n_probs=1):
     # wide designs: the heaviest 30 % of the cost-ordered grid as groups of M models of one fold on K-CTA clusters,
     # the light rest concurrently on the one-CTA-per-model kernel.  A model is a serial chain of 32-coordinate
     # blocks; measured per block for the heaviest model (profiles/r2_cd_experiments.txt): 6.1 us on (4,2), 4.0 us
-    # on (4,4), 3.4 us on (2,4) — wider clusters shorten the chain but need more SMs per model, so the shape follows
-    # the number of models this GPU holds: a share of a grid dealt over several GPUs gets the wide shapes throughout;
-    # a whole grid puts only its chain-critical head (the heaviest group of every problem: 4 models x n_probs) on
-    # (4,4) and the rest of the heavy part on (4,2) — the launch is then bound by SM time, not by the longest chain
-    # (1500 models: 354 -> 288 ms, experiments log section 7).
+    # on (4,4), 3.4 us on (2,4), 3.2 us on (1,8) — wider clusters shorten the chain but need more SMs per model.  The
+    # block counts fall quickly with the rank in the cost order, so only the HEAD of the order (the heaviest group of
+    # every problem) is chain-critical and gets the widest shape the GPU can afford; the shapes behind it follow the SMs
+    # that are left (experiments log sections 7 and 15):
+    #   a whole grid (>= ~800 models):  head on (4,4), rest of the heavy part on (4,2)         1500 models: 354 -> 288 ms
+    #   a share of a grid (one of 2-4 GPUs): head on (2,4), then (4,4) while SMs last, then (4,2)  750: 231 -> 204, 375: 208 -> 180
+    #   a small share (one of 8 GPUs):  one model per problem on (1,8), the rest on (2,4)      188: 173 -> 163
     # A handful of models (a single GLM.fit) leaves the GPU idle anyway: each model gets a 4-CTA cluster
     # (config 1: CD 5.6 -> 4.3 ms).  Narrow designs keep one CTA per model.
     if C > 1024 and n_models >= 16:
-        heavy = 0.3 * n_models
-        for m, k, sm_budget in ((2, 4, 240), (4, 4, 240)):
-            if -(-heavy // m) * k <= sm_budget:
-                return f"{m}x{k}@0.3,0x0"
-        head = 4 * max(1, n_probs)
+        P = max(1, n_probs)
+        heavy = int(round(0.3 * n_models))
+        sms = 148
+        if n_models <= 250 and P <= heavy and 8 * P <= sms:
+            rest = heavy - P
+            return f"1x8#{P}," + (f"2x4#{rest}," if rest > 0 else "") + "0x0"
+        if n_models <= 800 and 4 * P <= heavy and 8 * P <= sms:
+            head = 4 * P                                   # groups of 2 on 4 CTAs: 2 CTAs per model
+            rest = heavy - head
+            left = int(1.15 * sms) - 2 * head              # CTAs the GPU can still hold at once (slightly oversubscribed)
+            n44 = max(0, min(rest, 2 * left - rest))       # (4,4): 1 CTA per model, (4,2): half a CTA per model
+            n44 = (n44 + 2 * P) // (4 * P) * (4 * P) if n44 < rest else rest
+            n44 = min(n44, rest)
+            n42 = rest - n44
+            return (f"2x4#{head}," + (f"4x4#{n44}," if n44 > 0 else "") + (f"4x2#{n42}," if n42 > 0 else "") + "0x0")
+        head = 4 * P
         if head <= 0.1 * n_models:
-            return f"4x4#{head},4x2#{int(round(heavy)) - head},0x0"
+            return f"4x4#{head},4x2#{heavy - head},0x0"
         return "4x2@0.3,0x0"
     if C >= 256 and n_models <= 8:
         return "1x4"

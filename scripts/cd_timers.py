@@ -32,7 +32,7 @@ def run(plan, sel, models):
     h = np.argsort(-info[:, 4])[:3]
     return dt, info[h, 4], info[h, 5], info[:, 3].sum()
 for item in os.environ.get("DIAG_PLANS", "4x2@0.3,0x0").split(";"):
-    plan, _, var = item.partition("#")
+    plan, _, var = item.partition("!")
     os.environ["SGLM_TUNING"] = "1"
     os.environ["SGLM_CDC_VARIANT"] = var or "0"
     for every in [int(v) for v in os.environ.get('DIAG_EVERY', '1,2,8').split(',')]:

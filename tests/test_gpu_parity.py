@@ -650,7 +650,7 @@ def test_config3_elasticnet_cv_grid_vs_oracle():
                                   engine="sklearn")
     got = sglm_cv.cv_glm_mult_params(Xd, y, cv_idx, "Gaussian", [dict(g) for g in grid], score_method="r2")
     assert nat.last_tc_plan["cells"]                                       # overlapping folds went through the cells
-    assert eng._cd_plan(1200, len(grid) * 4)[0][2] >= 2                    # ... and the heavy models through clusters
+    assert eng._cd_plan(1200, len(grid) * 4, 4)[0][3] >= 2                 # ... and the heavy models through clusters
     assert got["best_params"] == want["best_params"]
     assert abs(got["best_score"] - want["best_score"]) < 1e-6
     for a, b in zip(got["full_cv_results"], want["full_cv_results"]):

@@ -170,7 +170,10 @@ def test_cd_launch_plan_parsing():
         assert eng._cd_plan(2000, 1500)[0][2:] == (4, 4)
         # a whole grid: the heaviest group of every problem on (4,4), the rest of the heavy 30 % on (4,2)
         assert eng._cd_plan(2000, 1500, 6) == [(0, 24, 4, 4), (24, 450, 4, 2), (450, 1500, 0, 0)]
-        assert eng._cd_plan(2000, 188, 6) == [(0, 56, 2, 4), (56, 188, 0, 0)]      # an eighth of a grid: wide clusters
+        # shares of a grid (one of several GPUs): the chain-critical head on the widest shape, then what the SMs allow
+        assert eng._cd_plan(2000, 750, 6) == [(0, 24, 2, 4), (24, 72, 4, 4), (72, 225, 4, 2), (225, 750, 0, 0)]
+        assert eng._cd_plan(2000, 375, 6) == [(0, 24, 2, 4), (24, 112, 4, 4), (112, 375, 0, 0)]
+        assert eng._cd_plan(2000, 188, 6) == [(0, 6, 1, 8), (6, 56, 2, 4), (56, 188, 0, 0)]
         eng.CD_PLAN = "4x4#24,4x2#100,0x0"
         assert eng._cd_plan(2000, 1500) == [(0, 24, 4, 4), (24, 124, 4, 2), (124, 1500, 0, 0)]
         eng.CD_PLAN = None
